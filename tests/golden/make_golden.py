@@ -1,0 +1,176 @@
+"""Generate golden input/output vectors from the UNMODIFIED reference (build container only).
+
+The reference (pure Python, /root/reference/gpyrn) needs jax, emcee and matplotlib, none of
+which exist in this image, and trips over numpy>=2 (``np.float``).  It runs from its own
+sources once stand-in modules are registered for those imports: ``jax.numpy`` backed by numpy,
+``jax.jit`` as identity, ``jax.scipy.linalg.cho_solve`` = scipy's.
+Arithmetic deviation from real JAX is rounding-level only (LAPACK potrf/potrs either way).
+
+Run once:  python tests/golden/make_golden.py     (writes tests/golden/*.npz)
+The GPU box has no /root/reference; tests only read the committed .npz files.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import scipy.linalg
+
+REF = os.environ.get("GPYRN_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def install_shim():
+    def mod(name, **kw):
+        m = types.ModuleType(name)
+        m.__dict__.update(kw)
+        sys.modules[name] = m
+        return m
+
+    def jit(f=None, static_argnums=None, **kw):
+        return (lambda g: g) if f is None else f
+
+    jnp = mod("jax.numpy")
+    jnp.__dict__.update({k: getattr(np, k) for k in dir(np) if not k.startswith("_")})
+    jnp.ndarray = np.ndarray
+    jsl = mod("jax.scipy.linalg", cho_solve=scipy.linalg.cho_solve)
+    js = mod("jax.scipy", linalg=jsl)
+
+    class _Cfg:
+        def update(self, *a, **k):
+            pass
+
+    mod("jax", jit=jit, numpy=jnp, scipy=js, config=_Cfg())
+    mpl = mod("matplotlib")
+    mpl.pyplot = mod("matplotlib.pyplot")
+    em = mod("emcee", EnsembleSampler=object, backends=types.SimpleNamespace())
+    em.utils = mod("emcee.utils", sample_ellipsoid=None)
+    if not hasattr(np, "float"):
+        np.float = float
+    sys.path.insert(0, REF)
+
+
+install_shim()
+from gpyrn import covfunc, meanfunc, meanfield  # noqa: E402  (the reference itself)
+
+KCLS = {"SE": covfunc.SquaredExponential, "P": covfunc.Periodic, "QP": covfunc.QuasiPeriodic,
+        "RQ": covfunc.RationalQuadratic, "M32": covfunc.Matern32, "M52": covfunc.Matern52,
+        "WN": covfunc.WhiteNoise}
+
+
+def build_kernel(spec):
+    if spec[0] == "sum":
+        return build_kernel(spec[1]) + build_kernel(spec[2])
+    if spec[0] == "mul":
+        return build_kernel(spec[1]) * build_kernel(spec[2])
+    return KCLS[spec[0]](*spec[1:])
+
+
+def spec_to_arr(spec):
+    """Serialise a spec as a string (np.savez friendly)."""
+    return repr(spec)
+
+
+def run_case(name, t, ys, es, nodes, weights, mean_consts, jitters, max_iter=None, tstar=None):
+    q = len(nodes)
+    args = []
+    for y, e in zip(ys, es):
+        args += [y, e]
+    g = meanfield.inference(q, t, *args)
+    g.set_components([build_kernel(s) for s in nodes], [build_kernel(s) for s in weights],
+                     [meanfunc.Constant(c) for c in mean_consts], list(jitters))
+    # per-iteration trace: wrap ELBOaux
+    trace = []
+    orig = g.ELBOaux
+
+    def rec(*a, **k):
+        out = orig(*a, **k)
+        trace.append(float(out[0]))
+        return out
+
+    g.ELBOaux = rec
+    elbo, mu, var, it = g.ELBOcalc(max_iter=max_iter)
+    out = dict(t=t, y=np.array(ys), yerr=np.array(es), nodes=np.array([spec_to_arr(s) for s in nodes]),
+               weights=np.array([spec_to_arr(s) for s in weights]), mean_consts=np.array(mean_consts, float),
+               jitters=np.array(jitters, float), elbo=float(elbo), mu=np.asarray(mu), var=np.asarray(var),
+               iters=int(it), trace=np.array(trace), max_iter=-1 if max_iter is None else max_iter)
+    if tstar is not None:
+        pm, pv, sep = g._Prediction(tstar=tstar, mu=np.asarray(mu), var=np.asarray(var), separate=True)
+        out.update(tstar=tstar, pred_mean=pm, pred_var=pv, node_pred=np.array(sep[0], float),
+                   weight_pred=np.array(sep[1], float))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: ELBO={elbo!r} iters={it}")
+
+
+def synth_data(N, p, seed=1):
+    rng = np.random.default_rng(seed)
+    t = np.sort(rng.uniform(0, 4 * N ** 0.5 * 10, N))
+    ys, es = [], []
+    for i in range(p):
+        ys.append(np.sin(2 * np.pi * t / 25 + i) * (1 + 0.3 * i) + 0.1 * rng.standard_normal(N))
+        es.append(rng.uniform(.05, .15, N))
+    return t, ys, es
+
+
+def synth_case(name, N, p, q, node="QP", means=None, max_iter=None, T=None):
+    t, ys, es = synth_data(N, p)
+    if node == "QP":
+        nodes = [("QP", 1 + .2 * j, 60 + 5 * j, 25 + j, .7) for j in range(q)]
+    else:
+        nodes = [("M52", 1 + .2 * j, 30 + 5 * j) for j in range(q)]
+    weights = [("SE", 1 + .1 * k, 80 + k) for k in range(q * p)]
+    tstar = None if T is None else np.linspace(t[0] - 5.0, t[-1] + 5.0, T)
+    run_case(name, t, ys, es, nodes, weights, means or [0.0] * p, [0.1] * p, max_iter=max_iter, tstar=tstar)
+
+
+def kernel_vectors():
+    """Element-wise k(r) of every in-scope kernel (+Sum, Multiplication) on a fixed lag grid."""
+    rng = np.random.default_rng(7)
+    t = np.sort(rng.uniform(0, 100, 40))
+    ts = np.linspace(-3, 104, 23)
+    specs = [("SE", 1.3, 11.0), ("P", 0.9, 17.0, 0.8), ("QP", 1.1, 35.0, 23.0, 0.6), ("RQ", 1.2, 0.7, 9.0),
+             ("M32", 0.8, 14.0), ("M52", 1.4, 21.0), ("WN", 0.3),
+             ("sum", ("SE", 1.0, 10.0), ("WN", 0.2)), ("mul", ("SE", 1.0, 10.0), ("P", 1.0, 20.0, 0.5)),
+             ("sum", ("mul", ("M52", 1.1, 30.0), ("P", 1.0, 12.0, 0.9)), ("RQ", 0.5, 1.5, 40.0))]
+    out = dict(t=t, tstar=ts, specs=np.array([repr(s) for s in specs]))
+    for i, s in enumerate(specs):
+        k = build_kernel(s)
+        out[f"Ksq_{i}"] = k(t[:, None] - t[None, :])
+        out[f"Krect_{i}"] = k(ts[:, None] - t[None, :])
+    np.savez_compressed(os.path.join(HERE, "kernels.npz"), **out)
+    print("kernels: ok")
+
+
+def main():
+    kernel_vectors()
+    # notebook data (docs/examples/one_dataset.ipynb; SURVEY.md 8c anchor -267.06958539495247, 4 it)
+    from scipy.stats import norm
+    np.random.seed(43)
+    t = np.sort(np.random.uniform(10, 60, 45))
+    y = 1.5 * np.sin(2 * np.pi * t / 13.5) * np.polyval([0.01, 0.02, 2.5], t)
+    yerr = np.random.uniform(2, 5, 45)
+    y = y + norm(0, np.hypot(0.5, yerr)).rvs()
+    run_case("notebook_45_1_1", t, [y], [yerr], [("P", 1, 13, 1)], [("SE", 1, 50)], [0.0], [0.1],
+             tstar=np.linspace(5, 65, 77))
+    # C1: bundled solar RV data, (497,1,1)
+    d = np.loadtxt(os.path.join(REF, "gpyrn", "datasets", "Solar_observations.txt"), skiprows=1)
+    t, rv, rve = d[:, 0].copy(), d[:, 1].copy(), d[:, 2].copy()
+    run_case("c1_solar_497_1_1", t, [rv], [rve], [("QP", 1, 30, 27, 0.7)], [("SE", 2, 200)], [rv.mean()], [0.5],
+             tstar=np.linspace(t[0], t[-1], 200))
+    synth_case("synth_50_1_1_QP", 50, 1, 1, T=31)
+    synth_case("synth_100_4_1_QP", 100, 4, 1, T=64)
+    synth_case("synth_60_2_2_QP_means", 60, 2, 2, means=[0.3, 0.6], T=50)
+    synth_case("synth_100_4_2_M52_means", 100, 4, 2, node="M52", means=[0.3, 0.6, 0.9, 1.2], T=40)
+    synth_case("c3_synth_256_4_1_QP", 256, 4, 1)
+    synth_case("synth_256_4_2_M52", 256, 4, 2, node="M52", T=100)
+    synth_case("c2_synth_500_4_1_QP", 500, 4, 1, T=128)
+    # mixed kernels: exercises every in-scope tag through the whole ELBO path
+    t, ys, es = synth_data(80, 2, seed=5)
+    run_case("mixed_80_2_2", t, ys, es,
+             [("sum", ("M32", 1.0, 40.0), ("WN", 0.05)), ("mul", ("SE", 1.1, 70.0), ("P", 1.0, 25.0, 0.8))],
+             [("RQ", 1.0, 0.9, 60.0), ("M52", 1.1, 90.0), ("P", 0.9, 33.0, 1.1), ("SE", 1.2, 75.0)],
+             [0.1, -0.2], [0.12, 0.08], tstar=np.linspace(t[0], t[-1] + 10, 45))
+
+
+if __name__ == "__main__":
+    main()
