@@ -1,0 +1,170 @@
+// assemble.cuh -- covariance-matrix assembly kernels (HBM-write bound).
+//
+// One thread evaluates k(t_i - t_j) for 16 elements of a 64x64 tile; the time stamps of the tile's
+// rows and columns are staged in shared memory, stores are coalesced along the column index.
+// The kernel function is a postfix program (opcodes of include/gprn_b200.h) interpreted per
+// element; every thread of a CTA follows the same control path, so there is no divergence.
+// Floating-point expressions follow the operation order of gpyrn/covfunc.py so that results agree
+// with numpy to a few ulp.
+#pragma once
+#include "common.cuh"
+#include "../../include/gprn_b200.h"
+
+namespace gprn {
+
+struct ProgTable {  // device pointers, one entry per matrix m of the model (nodes first, then weights)
+    const int32_t* tok;      // [M][GPRN_MAX_PROG]
+    const int32_t* len;      // [M]
+    const int32_t* par_off;  // [M] offset of the matrix' first parameter inside a hyper set
+};
+
+// k(r).  `on_diag_pos`: element sits on the main diagonal by POSITION (WhiteNoise quirk Q9,
+// covfunc.py:144-148); `wn_const`: rectangular evaluation -> WhiteNoise is the constant w^2.
+__device__ __forceinline__ double eval_prog(const int32_t* __restrict__ tok, int ntok, const double* __restrict__ par,
+                                            double r, bool on_diag_pos, bool wn_const) {
+    double st[6];
+    int sp = 0, pp = 0;
+    const double ar = fabs(r);
+    for (int t = 0; t < ntok; t++) {
+        const int op = tok[t];
+        switch (op) {
+            case GPRN_OP_SE: {  // covfunc.py:169-170
+                double th = par[pp], l = par[pp + 1];
+                st[sp++] = (th * th) * exp(((-0.5) * (r * r)) / (l * l));
+                pp += 2;
+            } break;
+            case GPRN_OP_PER: {  // covfunc.py:211-213
+                double th = par[pp], P = par[pp + 1], l = par[pp + 2];
+                double s = sin((M_PI * ar) / P);
+                st[sp++] = (th * th) * exp(((-2.0) * (s * s)) / (l * l));
+                pp += 3;
+            } break;
+            case GPRN_OP_QP: {  // covfunc.py:251-255
+                double th = par[pp], le = par[pp + 1], P = par[pp + 2], lp = par[pp + 3];
+                double s = sin((M_PI * ar) / P);
+                double t1 = ((-2.0) * (s * s)) / (lp * lp);
+                double t2 = (r * r) / (2.0 * (le * le));
+                st[sp++] = (th * th) * exp(t1 - t2);
+                pp += 4;
+            } break;
+            case GPRN_OP_RQ: {  // covfunc.py:286-288
+                double th = par[pp], al = par[pp + 1], l = par[pp + 2];
+                st[sp++] = (th * th) * pow(1.0 + (0.5 * (r * r)) / (al * (l * l)), -al);
+                pp += 3;
+            } break;
+            case GPRN_OP_M32: {  // covfunc.py:370-373
+                double th = par[pp], l = par[pp + 1];
+                double s = (sqrt(3.0) * ar) / l;
+                st[sp++] = ((th * th) * (1.0 + s)) * exp(-s);
+                pp += 2;
+            } break;
+            case GPRN_OP_M52: {  // covfunc.py:391-396
+                double th = par[pp], l = par[pp + 1];
+                double num = ((3.0 * sqrt(5.0)) * l) * ar + 5.0 * (ar * ar);
+                st[sp++] = ((th * th) * (1.0 + num / (3.0 * (l * l)))) * exp((-sqrt(5.0) * ar) / l);
+                pp += 2;
+            } break;
+            case GPRN_OP_WN: {  // covfunc.py:144-148
+                double w = par[pp];
+                st[sp++] = (on_diag_pos || wn_const) ? w * w : 0.0;
+                pp += 1;
+            } break;
+            case GPRN_OP_ADD: {
+                sp--;
+                st[sp - 1] = st[sp - 1] + st[sp];
+            } break;
+            case GPRN_OP_MUL: {
+                sp--;
+                st[sp - 1] = st[sp - 1] * st[sp];
+            } break;
+            default: break;
+        }
+    }
+    return st[0];
+}
+
+// Symmetric assembly of K_m = k_m(t - t^T) + nugget*I for every matrix of every set in the chunk.
+// grid = (nt*(nt+1)/2 lower tiles, M, nset), block = 256.  Writes tiles I >= J; diagonal tiles full.
+// Padding (index >= N): identity.
+__global__ void __launch_bounds__(256) kassemble_sym_kernel(double* __restrict__ K, const double* __restrict__ time,
+                                                            const double* __restrict__ hyper, int H, ProgTable pt,
+                                                            int M, int N, int Np, double nugget) {
+    __shared__ double ti[NB], tj[NB];
+    __shared__ int32_t stok[GPRN_MAX_PROG];
+    __shared__ double spar[GPRN_MAX_PROG * 4];
+    int I, J;
+    tri_decode(blockIdx.x, I, J);
+    const int m = blockIdx.y, set = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int ntok = pt.len[m];
+    if (tid < NB) {
+        int gi = I * NB + tid, gj = J * NB + tid;
+        ti[tid] = gi < N ? time[gi] : 0.0;
+        tj[tid] = gj < N ? time[gj] : 0.0;
+    }
+    if (tid < ntok) stok[tid] = pt.tok[m * GPRN_MAX_PROG + tid];
+    if (tid < GPRN_MAX_PROG * 4) {
+        int po = pt.par_off[m] + tid;
+        spar[tid] = po < H ? hyper[(size_t)set * H + po] : 0.0;
+    }
+    __syncthreads();
+    double* Kt = K + ((size_t)set * M + m) * Np * Np;
+    const int c = tid & 63, rg = tid >> 6;
+    const int gj = J * NB + c;
+#pragma unroll 4
+    for (int u = 0; u < 16; u++) {
+        const int rr = rg * 16 + u, gi = I * NB + rr;
+        double v;
+        if (gi < N && gj < N) {
+            v = eval_prog(stok, ntok, spar, ti[rr] - tj[c], gi == gj, false);
+            if (gi == gj) v += nugget;
+        } else {
+            v = (gi == gj) ? 1.0 : 0.0;
+        }
+        Kt[(size_t)gi * Np + gj] = v;
+    }
+}
+
+// Rectangular assembly K[r][c] = k(trow[r] - tcol[c]) (+ nugget on the diagonal when `square`),
+// row-major with leading dimension ld, no padding.  grid = (ceil(ncols/64), ceil(nrows/64)), block 256.
+// Used for Kstar (prediction) and for gprn_kmatrix.
+__global__ void __launch_bounds__(256) kassemble_rect_kernel(double* __restrict__ K, size_t ld,
+                                                             const double* __restrict__ trow, int nrows,
+                                                             const double* __restrict__ tcol, int ncols,
+                                                             const int32_t* __restrict__ tok, int ntok,
+                                                             const double* __restrict__ par, int npar, int square,
+                                                             double nugget) {
+    __shared__ double ti[NB], tj[NB];
+    __shared__ int32_t stok[GPRN_MAX_PROG];
+    __shared__ double spar[GPRN_MAX_PROG * 4];
+    const int tid = threadIdx.x;
+    if (tid < NB) {
+        int gi = blockIdx.y * NB + tid, gj = blockIdx.x * NB + tid;
+        ti[tid] = gi < nrows ? trow[gi] : 0.0;
+        tj[tid] = gj < ncols ? tcol[gj] : 0.0;
+    }
+    if (tid < ntok) stok[tid] = tok[tid];
+    if (tid < GPRN_MAX_PROG * 4) spar[tid] = tid < npar ? par[tid] : 0.0;
+    __syncthreads();
+    const int c = tid & 63, rg = tid >> 6;
+    const int gj = blockIdx.x * NB + c;
+    if (gj >= ncols) return;
+    for (int u = 0; u < 16; u++) {
+        const int rr = rg * 16 + u, gi = blockIdx.y * NB + rr;
+        if (gi >= nrows) break;
+        double v = eval_prog(stok, ntok, spar, ti[rr] - tj[c], square && gi == gj, !square);
+        if (square && gi == gj) v += nugget;
+        K[(size_t)gi * ld + gj] = v;
+    }
+}
+
+// out[e] = k(r[e]) for an arbitrary array of lags (covFunction.__call__).  1-D grid-stride.
+__global__ void keval_kernel(double* __restrict__ out, const double* __restrict__ r, long long n, long long ncols,
+                             const int32_t* __restrict__ tok, int ntok, const double* __restrict__ par, int square) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        bool dg = square && (e / ncols == e % ncols);
+        out[e] = eval_prog(tok, ntok, par, r[e], dg, !square);
+    }
+}
+
+}  // namespace gprn

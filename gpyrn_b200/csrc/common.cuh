@@ -1,0 +1,145 @@
+// common.cuh -- shared device helpers for the GPRN hot path (sm_100a, FP64).
+//
+// Layout conventions (see DESIGN.md "Data layout in HBM"):
+//   * every dense matrix is row-major, Np x Np with Np = N rounded up to a multiple of the tile
+//     size NB = 64; the padding block is the identity, so Cholesky factors / inverses / log-dets of
+//     the padded matrix restrict exactly to those of the N x N matrix;
+//   * only the lower triangle (tiles I >= J) is ever read or written, diagonal tiles are stored full;
+//   * a batch of matrices is addressed through a device array of matrix ids: matrix `id` lives at
+//     base + id * Np * Np, its work vectors at base + id * Np.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define NB 64           // tile size
+#define LDT 68          // shared-memory row stride (doubles) of an MMA operand tile: 68*8 B = 32 (mod 128)
+                        // -> the m8n8k4 fragment loads of a half-warp hit 16 distinct 8-byte slots
+#define LDV 65          // odd stride for tiles accessed one-vector-per-thread (conflict free both ways)
+#define TILE_SMEM (NB * LDT * sizeof(double))
+
+namespace gprn {
+
+// D(8x8) += A(8x4) * B(4x8), FP64 tensor-core path (SASS: DMMA.8x8x4).
+// a = A[lane/4][lane%4], b = B[lane%4][lane/4], c = {C[lane/4][2*(lane%4)], C[lane/4][2*(lane%4)+1]}.
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
+// Load a 64x64 tile from global memory (row-major, leading dimension ld) into shared memory
+// dst[64][LDT].  TRANS: dst[m][k] = src[k*ld + m].  `scale` (optional, length 64) multiplies along
+// the k index of dst (used for the D-weighted cross term).  All `nthreads` threads of the CTA call.
+template <bool TRANS>
+__device__ __forceinline__ void load_tile(double* __restrict__ dst, const double* __restrict__ src, size_t ld,
+                                          int tid, int nthreads, const double* __restrict__ scale = nullptr) {
+    if (!TRANS) {
+        // 64 rows x 32 double2
+        for (int e = tid; e < NB * (NB / 2); e += nthreads) {
+            int r = e >> 5, c2 = e & 31;
+            double2 v = *reinterpret_cast<const double2*>(src + (size_t)r * ld + 2 * c2);
+            if (scale) { v.x *= scale[2 * c2]; v.y *= scale[2 * c2 + 1]; }
+            *reinterpret_cast<double2*>(dst + r * LDT + 2 * c2) = v;
+        }
+    } else {
+        for (int e = tid; e < NB * NB; e += nthreads) {
+            int k = e >> 6, m = e & 63;          // coalesced along m in global memory
+            double v = src[(size_t)k * ld + m];
+            if (scale) v *= scale[k];
+            dst[m * LDT + k] = v;
+        }
+    }
+}
+
+// acc(32x32 warp tile) += As(rows wm*32.., k 0..63) * Bs(rows wn*32.., k 0..63)^T, with As/Bs in
+// shared memory [64][LDT].  NEG: subtract instead (a fragment negated).
+template <bool NEG>
+__device__ __forceinline__ void mma_tile(double (&acc)[4][4][2], const double* __restrict__ As,
+                                         const double* __restrict__ Bs, int wm, int wn, int lane) {
+    const int r = lane >> 2, c = lane & 3;
+    const double* ap = As + (wm * 32 + r) * LDT + c;
+    const double* bp = Bs + (wn * 32 + r) * LDT + c;
+#pragma unroll 4
+    for (int k0 = 0; k0 < NB; k0 += 4) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            a[i] = ap[i * 8 * LDT + k0];
+            if (NEG) a[i] = -a[i];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) b[j] = bp[j * 8 * LDT + k0];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j], a[i], b[j]);
+    }
+}
+
+// Forward substitution  L y = g  for ONE vector per thread, everything in shared memory.
+//   Ls : 64x64 lower-triangular tile, element (m,k) at Ls[m*lds + k]   (read by broadcast)
+//   V  : vectors, element m of vector n at V[m*ldv + n]
+//   first_block : rows below first_block*8 are known to be zero on input (identity right-hand sides)
+// Blocked by 8 so that the 8 running values stay in registers; divisions (not reciprocal
+// multiplications) as in LAPACK dtrsm -- see DESIGN.md "Numerics" for why this matters here.
+__device__ __forceinline__ void subst_lower(const double* __restrict__ Ls, int lds, double* __restrict__ V,
+                                            int ldv, int n, int first_block = 0) {
+    for (int mb = first_block; mb < 8; mb++) {
+        double y[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) y[u] = V[(mb * 8 + u) * ldv + n];
+        for (int kb = first_block; kb < mb; kb++) {
+            double x[8];
+#pragma unroll
+            for (int w = 0; w < 8; w++) x[w] = V[(kb * 8 + w) * ldv + n];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const double* lrow = Ls + (mb * 8 + u) * lds + kb * 8;
+#pragma unroll
+                for (int w = 0; w < 8; w++) y[u] = fma(-lrow[w], x[w], y[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const double* lrow = Ls + (mb * 8 + u) * lds + mb * 8;
+#pragma unroll
+            for (int w = 0; w < u; w++) y[u] = fma(-lrow[w], y[w], y[u]);
+            y[u] = y[u] / lrow[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) V[(mb * 8 + u) * ldv + n] = y[u];
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum (blockDim.x <= 1024, multiple of 32); result valid in every thread.
+__device__ __forceinline__ double block_sum(double v, double* red /* >= 33 doubles of shared memory */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = lane < nw ? red[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+// linear index over the lower triangle (including diagonal) of an n x n tile grid -> (I, J), I >= J
+__device__ __forceinline__ void tri_decode(int t, int& I, int& J) {
+    int i = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= t) i++;
+    while (i * (i + 1) / 2 > t) i--;
+    I = i;
+    J = t - i * (i + 1) / 2;
+}
+
+}  // namespace gprn

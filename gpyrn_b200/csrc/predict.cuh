@@ -1,0 +1,110 @@
+// predict.cuh -- GP conditional mean / variance at T test epochs (gpyrn/_gp.py:107-138) and the GPRN
+// combination step (gpyrn/meanfield.py:1364-1372).
+//
+// The reference loops over the T test points, doing a 1-RHS cho_solve and a T x N dgemv per point and
+// keeping only the diagonal of a T x T matrix.  Here, with X = chol(K + diag(v))^-1:
+//     mean[t] = Kstar[t,:] . alpha,  alpha = X^T X m
+//     var[t]  = k(0) + 1.25e-12 - || X Kstar[t,:]^T ||^2
+// Kstar is assembled in chunks of test points; the squared norms come from a DMMA product
+// Kstar_chunk * X^T whose 64x64 output tiles are squared and row-reduced in registers, never stored.
+#pragma once
+#include "common.cuh"
+#include "assemble.cuh"
+
+namespace gprn {
+
+// out[t] = sum_n Ks[t][n] * alpha[n].  One warp per row.  grid = (ceil(T/8)), block = 256.
+__global__ void __launch_bounds__(256) rect_gemv_kernel(double* __restrict__ out, const double* __restrict__ Ks,
+                                                        size_t ld, const double* __restrict__ alpha, int T, int N) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 8 + warp;
+    if (t >= T) return;
+    const double* row = Ks + (size_t)t * ld;
+    double s = 0.0;
+    for (int n = lane; n < N; n += 32) s = fma(row[n], alpha[n], s);
+    s = warp_sum(s);
+    if (lane == 0) out[t] = s;
+}
+
+// rownorm2[t] = sum_a ( sum_{n<=a} Ks[t][n] X[a][n] )^2 for the 64 test rows of this CTA.
+// Ks: [Tpad][Np] (columns >= N zero, rows >= T zero), X: [Np][Np] lower.  grid = (Tpad/64), block = 128,
+// dynamic shared memory 2*TILE_SMEM.
+__global__ void __launch_bounds__(128) predict_norm_kernel(double* __restrict__ rownorm2,
+                                                           const double* __restrict__ Ks,
+                                                           const double* __restrict__ X, int Np, int N) {
+    extern __shared__ double smem[];
+    double* As = smem;
+    double* Bs = smem + NB * LDT;
+    __shared__ double rs[2][NB];
+    const int nt = Np / NB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1;
+    const int r = lane >> 2, cc = lane & 3;
+    const double* Kt = Ks + (size_t)(blockIdx.x * NB) * Np;
+    double rowacc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int a = 0; a < nt; a++) {
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int kt = 0; kt <= a; kt++) {
+            load_tile<false>(As, Kt + kt * NB, Np, tid, 128);
+            load_tile<false>(Bs, X + (size_t)(a * NB) * Np + kt * NB, Np, tid, 128);
+            __syncthreads();
+            mma_tile<false>(acc, As, Bs, wm, wn, lane);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int ga = a * NB + wn * 32 + j * 8 + 2 * cc;      // identity padding of X must not count
+                if (ga < N) rowacc[i] = fma(acc[i][j][0], acc[i][j][0], rowacc[i]);
+                if (ga + 1 < N) rowacc[i] = fma(acc[i][j][1], acc[i][j][1], rowacc[i]);
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double s = rowacc[i];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (cc == 0) rs[wn][wm * 32 + i * 8 + r] = s;
+    }
+    __syncthreads();
+    if (tid < NB) rownorm2[blockIdx.x * NB + tid] = rs[0][tid] + rs[1][tid];
+}
+
+// var[t] = k(0) + nugget - rownorm2[t]   (diagonal of Kstarstar, _gp.py:131,136-137)
+__global__ void predict_var_kernel(double* __restrict__ var, const double* __restrict__ rownorm2, int T,
+                                   const int32_t* __restrict__ tok, int ntok, const double* __restrict__ par,
+                                   double nugget) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    double k0 = eval_prog(tok, ntok, par, 0.0, true, false) + nugget;
+    var[t] = k0 - rownorm2[t];
+}
+
+// GPRN combination (meanfield.py:1364-1372; jitter^2 added once per node, quirk Q6).
+// gp_mean/gp_var: [M][T] (m = j nodes, q + j*p + i weights).  out mean/var: [T][p].
+__global__ void predict_combine_kernel(double* __restrict__ pmean, double* __restrict__ pvar,
+                                       const double* __restrict__ gp_mean, const double* __restrict__ gp_var,
+                                       const double* __restrict__ mean_t, const double* __restrict__ jit, int T,
+                                       int p, int q) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= T * p) return;
+    int t = e / p, i = e % p;
+    double m = 0.0, v = 0.0;
+    m += mean_t[(size_t)i * T + t];
+    double j2 = jit[i] * jit[i];
+    for (int j = 0; j < q; j++) {
+        double nP = gp_mean[(size_t)j * T + t], nV = gp_var[(size_t)j * T + t];
+        size_t w = (size_t)(q + j * p + i) * T + t;
+        double wP = gp_mean[w], wV = gp_var[w];
+        m += nP * wP;
+        v += ((wP * wP) * nV + wV * (nV + nP * nP)) + j2;
+    }
+    pmean[e] = m;
+    pvar[e] = v;
+}
+
+}  // namespace gprn

@@ -1,0 +1,87 @@
+"""Sharding of independent ELBO evaluations over the GPUs of one box.
+
+The path has no data-path exchange: every hyper-parameter set is an independent ``ELBOcalc``
+(SURVEY.md 8e), the data (time, y, yerr) is replicated.  Rank r of G evaluates a contiguous or
+strided block of the B sets on its own GPU; the only collective is one all-gather of the B ELBO
+values (+ iteration counts) -- NCCL over NVLink when the ranks hold GPUs, gloo in the CPU tests of
+the partitioning logic.
+"""
+import numpy as np
+
+
+def shard_indices(B, world_size, rank, mode="strided"):
+    """Indices of the hyper-parameter sets evaluated by ``rank``.
+
+    ``strided`` (round-robin) evens out the spread of iteration counts across ranks when neighbouring
+    sets are similar; ``block`` keeps contiguous ranges."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    if mode == "strided":
+        return np.arange(rank, B, world_size)
+    if mode == "block":
+        base, rem = divmod(B, world_size)
+        start = rank * base + min(rank, rem)
+        return np.arange(start, start + base + (1 if rank < rem else 0))
+    raise ValueError(f"unknown shard mode {mode!r}")
+
+
+def gather_results(local_idx, local_vals, B, group=None, device=None):
+    """All-gather per-rank results into full length-B arrays on every rank.
+
+    ``local_vals`` is a dict name -> 1-D array aligned with ``local_idx``.  Uses torch.distributed
+    (backend of the default/``group`` process group: nccl on GPUs, gloo on CPU); without an
+    initialised process group it just scatters the local values (single process)."""
+    import torch
+    import torch.distributed as dist
+
+    out = {}
+    if not (dist.is_available() and dist.is_initialized()):
+        for k, v in local_vals.items():
+            full = np.zeros(B, dtype=np.asarray(v).dtype)
+            full[local_idx] = v
+            out[k] = full
+        return out
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                             if backend == "nccl" else torch.device("cpu"))
+    nmax = -(-B // world)
+    idx_t = torch.full((nmax,), -1, dtype=torch.int64, device=dev)
+    idx_t[: len(local_idx)] = torch.as_tensor(np.asarray(local_idx), dtype=torch.int64, device=dev)
+    idx_all = [torch.empty_like(idx_t) for _ in range(world)]
+    dist.all_gather(idx_all, idx_t, group=group)
+    for k, v in local_vals.items():
+        v = np.asarray(v)
+        tdt = torch.float64 if v.dtype.kind == "f" else torch.int64
+        buf = torch.zeros((nmax,), dtype=tdt, device=dev)
+        buf[: len(local_idx)] = torch.as_tensor(v.astype(np.float64 if tdt == torch.float64 else np.int64), device=dev)
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf, group=group)
+        full = np.zeros(B, dtype=v.dtype)
+        for ids, vals in zip(idx_all, parts):
+            ids = ids.cpu().numpy()
+            ok = ids >= 0
+            full[ids[ok]] = vals.cpu().numpy()[ok].astype(v.dtype)
+        out[k] = full
+    return out
+
+
+def elbo_batch_sharded(gprn, parameters, max_iter=None, mode="strided", group=None):
+    """Evaluate B hyper-parameter sets across all ranks of the process group; every rank returns the
+    full (elbo[B], iters[B], status[B]).  ``gprn`` is this rank's ``inference`` bound to its GPU."""
+    import torch.distributed as dist
+
+    P = np.atleast_2d(np.asarray(parameters, dtype=float))
+    B = P.shape[0]
+    if dist.is_available() and dist.is_initialized():
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    else:
+        world, rank = 1, 0
+    idx = shard_indices(B, world, rank, mode)
+    if len(idx):
+        elbo, iters, status = gprn.ELBO_batch(P[idx], max_iter=max_iter, return_info=True)
+    else:
+        elbo, iters, status = np.zeros(0), np.zeros(0, np.int32), np.zeros(0, np.int32)
+    res = gather_results(idx, {"elbo": elbo, "iters": iters.astype(np.int64), "status": status.astype(np.int64)}, B,
+                         group=group)
+    return res["elbo"], res["iters"], res["status"]

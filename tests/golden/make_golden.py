@@ -164,11 +164,14 @@ def main():
     synth_case("c3_synth_256_4_1_QP", 256, 4, 1)
     synth_case("synth_256_4_2_M52", 256, 4, 2, node="M52", T=100)
     synth_case("c2_synth_500_4_1_QP", 500, 4, 1, T=128)
-    # mixed kernels: exercises every in-scope tag through the whole ELBO path
+    # mixed kernels: exercises every in-scope tag through the whole ELBO path.  (A bare Periodic weight is
+    # avoided: K is then rank-deficient up to the nugget and the reference's own ELBO moves by 1e-9 relative
+    # under a 1-ulp change of the inputs, so it cannot anchor a 1e-10 parity test.)
     t, ys, es = synth_data(80, 2, seed=5)
     run_case("mixed_80_2_2", t, ys, es,
              [("sum", ("M32", 1.0, 40.0), ("WN", 0.05)), ("mul", ("SE", 1.1, 70.0), ("P", 1.0, 25.0, 0.8))],
-             [("RQ", 1.0, 0.9, 60.0), ("M52", 1.1, 90.0), ("P", 0.9, 33.0, 1.1), ("SE", 1.2, 75.0)],
+             [("RQ", 1.0, 0.9, 60.0), ("M52", 1.1, 90.0), ("mul", ("P", 0.9, 33.0, 1.1), ("M32", 1.0, 120.0)),
+              ("SE", 1.2, 75.0)],
              [0.1, -0.2], [0.12, 0.08], tstar=np.linspace(t[0], t[-1] + 10, 45))
 
 
