@@ -26,13 +26,14 @@ struct ElboCtx {
     double *Dv, *bv, *vv, *zv, *uv, *gv;  // [nset*M][Np]
     double *gK;              // [nset*M][Np] diag(K^-1) (q > 1 only)
     double *logdetK, *logdetA;  // [nset*M]
-    double *acc;             // [nset][ACC_N] per-set scalar accumulators
+    double *ment, *mlp, *mquad;  // [nset*M] per-matrix entropy / log-prior / quadratic-form pieces
+    double *cross_lin;       // [nset] linear part of the cross-node trace (q > 1)
+    double *crossbuf;        // [nset][q(q-1)/2][nt*nt] per-tile partials of the cross-node Frobenius norms
     double *hist;            // [nset][3] last three ELBO values
     double *elbo;            // [nset]
     int *iters, *status, *active, *mstatus;  // [nset], [nset], [nset], [nset*M]
     int max_iter;
 };
-enum { ACC_ENT = 0, ACC_LP = 1, ACC_N = 4 };
 
 __device__ __forceinline__ double variance_at(const ElboCtx& c, int set, int i, int n) {
     double jit = c.hyper[(size_t)set * c.H + c.H - c.p + i];
@@ -77,7 +78,6 @@ __global__ void init_state_kernel(ElboCtx c) {
         c.iters[set] = 0;
         c.status[set] = 0;
         c.active[set] = 1;
-        for (int k = 0; k < ACC_N; k++) c.acc[set * ACC_N + k] = 0.0;
     }
 }
 
@@ -170,8 +170,8 @@ __global__ void post_kernel(ElboCtx c, const int* __restrict__ sets, int first, 
     s_quad = block_sum(s_quad, red);
     if (threadIdx.x == 0) {
         double ldK = c.logdetK[id], ldA = c.logdetA[id];
-        atomicAdd(&c.acc[set * ACC_N + ACC_ENT], 0.5 * (ldK - ldA + s_logD));
-        atomicAdd(&c.acc[set * ACC_N + ACC_LP], -0.5 * ldK - 0.5 * (s_quad + s_Dg));
+        c.ment[id] = 0.5 * (ldK - ldA + s_logD);
+        c.mlp[id] = -0.5 * ldK - 0.5 * (s_quad + s_Dg);
         if (c.mstatus[id]) c.status[set] = 1;
     }
 }
@@ -185,7 +185,7 @@ __global__ void quad_kernel(ElboCtx c, const int* __restrict__ sets, int first) 
     double s = 0.0;
     for (int n = threadIdx.x; n < c.N; n += blockDim.x) s = fma(c.zv[vo + n], c.zv[vo + n], s);
     s = block_sum(s, red);
-    if (threadIdx.x == 0) atomicAdd(&c.acc[set * ACC_N + ACC_LP], -0.5 * s);
+    if (threadIdx.x == 0) c.mquad[(size_t)set * c.M + m] = -0.5 * s;
 }
 
 // Copy the vector that the reference pairs with K_m in the prior's quadratic form into vv (zero padded):
@@ -210,7 +210,7 @@ __global__ void cross_linear_kernel(ElboCtx c, const int* __restrict__ sets) {
             for (int n = threadIdx.x; n < c.N; n += blockDim.x) s = fma(Dk[n], gKj[n], s);
         }
     s = block_sum(s, red);
-    if (threadIdx.x == 0) atomicAdd(&c.acc[set * ACC_N + ACC_LP], -0.5 * s);
+    if (threadIdx.x == 0) c.cross_lin[set] = -0.5 * s;
 }
 
 // Cross-node trace, quadratic part: +0.5 * || X_Kj D_k X_Ak^T ||_F^2 for k < j.
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(128) cross_frob_kernel(ElboCtx c, const double
             }
         }
     s = block_sum(s, red);
-    if (tid == 0) atomicAdd(&c.acc[set * ACC_N + ACC_LP], 0.5 * s);
+    if (tid == 0) c.crossbuf[((size_t)set * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = 0.5 * s;
 }
 
 // Likelihood term, ELBO assembly, stopping rule, state commit.  grid = (nactive), block = 256.
@@ -291,6 +291,14 @@ __global__ void elbo_finish_kernel(ElboCtx c, const int* __restrict__ sets) {
     s_log = block_sum(s_log, red);
     s_res = block_sum(s_res, red);
     s_val = block_sum(s_val, red);
+    // per-matrix pieces summed in a fixed order (deterministic: no floating-point atomics on this path)
+    double s_cross = 0.0;
+    if (q > 1) {
+        const int ncross = (q * (q - 1) / 2) * (c.Np / NB) * (c.Np / NB);
+        const double* cb = c.crossbuf + (size_t)set * ncross;
+        for (int e = threadIdx.x; e < ncross; e += blockDim.x) s_cross += cb[e];
+        s_cross = block_sum(s_cross, red);
+    }
     // commit the new state (the reference carries new_mu/new_var into the next iteration, :636)
     const int commit = c.max_iter > 0;
     if (commit) {
@@ -305,13 +313,19 @@ __global__ void elbo_finish_kernel(ElboCtx c, const int* __restrict__ sets) {
         const double LOG2PI = log(2.0 * M_PI);
         const double MN = (double)c.M * (double)N;
         double ll = -0.5 * s_log - 0.5 * s_res - 0.5 * s_val;
-        double lp = c.acc[set * ACC_N + ACC_LP] - 0.5 * MN * LOG2PI;          // :1064
-        double ent = c.acc[set * ACC_N + ACC_ENT] + 0.5 * MN * (1.0 + LOG2PI);  // :1092
+        double lp = 0.0, ent = 0.0;
+        for (int m = 0; m < c.M; m++) {
+            const size_t id = (size_t)set * c.M + m;
+            ent += c.ment[id];
+            lp += c.mlp[id];
+            if (q > 1) lp += c.mquad[id];
+        }
+        if (q > 1) lp += c.cross_lin[set] + s_cross;
+        lp -= 0.5 * MN * LOG2PI;                     // :1064
+        ent += 0.5 * MN * (1.0 + LOG2PI);            // :1092
         double elbo = (ll + lp + ent) / q;                                       // :709
         if (c.status[set] == 1) elbo = nan("");
         c.elbo[set] = elbo;
-        c.acc[set * ACC_N + ACC_ENT] = 0.0;
-        c.acc[set * ACC_N + ACC_LP] = 0.0;
         double* hs = c.hist + set * 3;
         hs[0] = hs[1]; hs[1] = hs[2]; hs[2] = elbo;
         int it = c.iters[set];

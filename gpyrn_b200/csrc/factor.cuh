@@ -233,21 +233,20 @@ __global__ void __launch_bounds__(256) trmv_lower_kernel(double* __restrict__ z,
     if (lane == 0) z[(size_t)id * Np + a] = s;
 }
 
-// u[n] += sum_{a>=n} X[a][n] z[a],  g[n] += sum_{a>=n} X[a][n]^2   (u, g pre-zeroed; z may be null).
-// grid = (nt column tiles, ceil(Np/256) row chunks, nmat), block = 256 (64 columns x 4 row groups).
+// u[n] = sum_{a>=n} X[a][n] z[a],  g[n] = sum_{a>=n} X[a][n]^2   (z / u may be null).
+// One CTA owns a 64-column tile and walks all rows below it (fixed summation order: deterministic).
+// grid = (nt column tiles, nmat), block = 256 (64 columns x 4 row groups).
 __global__ void __launch_bounds__(256) trmv_upper_norm_kernel(double* __restrict__ u, double* __restrict__ g,
                                                               const double* __restrict__ X,
                                                               const double* __restrict__ z,
                                                               const int* __restrict__ ids, int Np) {
     __shared__ double su[4][NB], sg[4][NB];
-    const int id = ids[blockIdx.z];
+    const int id = ids[blockIdx.y];
     const int ct = blockIdx.x, n = ct * NB + (threadIdx.x & 63), rg = threadIdx.x >> 6;
-    const int a_lo = max(blockIdx.y * 256, ct * NB), a_hi = min((blockIdx.y + 1) * 256, Np);
-    if (a_lo >= a_hi) return;
     const double* Xm = X + (size_t)id * Np * Np;
     const double* zz = z ? z + (size_t)id * Np : nullptr;
     double pu = 0.0, pg = 0.0;
-    for (int a = a_lo + rg; a < a_hi; a += 4) {
+    for (int a = ct * NB + rg; a < Np; a += 4) {
         double x = Xm[(size_t)a * Np + n];
         pg = fma(x, x, pg);
         if (zz) pu = fma(x, zz[a], pu);
@@ -259,8 +258,8 @@ __global__ void __launch_bounds__(256) trmv_upper_norm_kernel(double* __restrict
         int cidx = threadIdx.x;
         pu = (su[0][cidx] + su[1][cidx]) + (su[2][cidx] + su[3][cidx]);
         pg = (sg[0][cidx] + sg[1][cidx]) + (sg[2][cidx] + sg[3][cidx]);
-        if (zz) atomicAdd(&u[(size_t)id * Np + n], pu);
-        atomicAdd(&g[(size_t)id * Np + n], pg);
+        if (zz) u[(size_t)id * Np + n] = pu;
+        g[(size_t)id * Np + n] = pg;
     }
 }
 

@@ -281,7 +281,7 @@ static int solve_batch(gprn_handle* h, const double* X, const int* d_ids, int nm
     (void)vec_elems;
     trmv_lower_kernel<<<dim3(Np / 8, nmat), 256, 0, st>>>(zv, X, vv, d_ids, nullptr, Np);
     LAUNCH_CHECK(h);
-    trmv_upper_norm_kernel<<<dim3(nt, (Np + 255) / 256, nmat), 256, 0, st>>>(uv, gv, X, zv, d_ids, Np);
+    trmv_upper_norm_kernel<<<dim3(nt, nmat), 256, 0, st>>>(uv, gv, X, zv, d_ids, Np);
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -311,8 +311,10 @@ static int setup_chunk(gprn_handle* h, int nset, Chunk& ck, bool ysub_per_set) {
     const size_t ve = (size_t)nset * M * Np;
     if (ensure(h->vecs, 7 * ve * sizeof(double))) return 1;
     if (ensure(h->state, 4 * (size_t)nset * h->d * sizeof(double))) return 1;
-    // small: logdetK, logdetA [nset*M]; acc [nset*4]; hist [nset*3]; elbo [nset] doubles; then ints
-    const size_t nd = 2 * (size_t)nset * M + (size_t)nset * (ACC_N + 3 + 1);
+    // small: logdetK, logdetA, ment, mlp, mquad [nset*M]; cross_lin [nset]; crossbuf [nset*npairs*nt*nt];
+    //        hist [nset*3]; elbo [nset] doubles; then ints
+    const size_t ncross = (size_t)(h->q * (h->q - 1) / 2) * h->nt * h->nt;
+    const size_t nd = 5 * (size_t)nset * M + (size_t)nset * (1 + ncross + 3 + 1);
     const size_t ni = 3 * (size_t)nset + (size_t)nset * M;
     if (ensure(h->small, nd * sizeof(double) + ni * sizeof(int))) return 1;
     const size_t nl = (size_t)nset * (1 + 2 * M);
@@ -338,9 +340,11 @@ static int setup_chunk(gprn_handle* h, int nset, Chunk& ck, bool ysub_per_set) {
     const size_t sd = (size_t)nset * h->d;
     c.mu = s; c.var = s + sd; c.mu_new = s + 2 * sd; c.var_new = s + 3 * sd;
     double* sm = (double*)h->small.p;
-    c.logdetK = sm; c.logdetA = sm + (size_t)nset * M;
-    c.acc = sm + 2 * (size_t)nset * M;
-    c.hist = c.acc + (size_t)nset * ACC_N;
+    const size_t nm = (size_t)nset * M;
+    c.logdetK = sm; c.logdetA = sm + nm; c.ment = sm + 2 * nm; c.mlp = sm + 3 * nm; c.mquad = sm + 4 * nm;
+    c.cross_lin = sm + 5 * nm;
+    c.crossbuf = c.cross_lin + nset;
+    c.hist = c.crossbuf + (size_t)nset * ncross;
     c.elbo = c.hist + (size_t)nset * 3;
     int* si = (int*)(c.elbo + nset);
     c.iters = si; c.status = si + nset; c.active = si + 2 * nset; c.mstatus = si + 3 * nset;
@@ -387,14 +391,11 @@ static int run_chunk(gprn_handle* h, Chunk& ck, bool init_given, int max_iter, c
     LAUNCH_CHECK(h);
     CU(cudaMemsetAsync(c.logdetK, 0, sizeof(double) * (size_t)nset * M, st));
     CU(cudaMemsetAsync(c.mstatus, 0, sizeof(int) * (size_t)nset * M, st));
-    CU(cudaMemsetAsync(c.acc, 0, sizeof(double) * (size_t)nset * ACC_N, st));
     form_a_kernel<<<dim3(ntri, nset * M), 256, 0, st>>>(ck.W, ck.K, nullptr, ck.d_ids_all, Np);
     LAUNCH_CHECK(h);
     if (factor_batch(h, ck.W, ck.d_ids_all, nset * M, c.logdetK, c.mstatus, q > 1 ? ck.XK : nullptr, st)) return 1;
     if (q > 1) {
-        CU(cudaMemsetAsync(c.gK, 0, sizeof(double) * ck.vec_elems, st));
-        trmv_upper_norm_kernel<<<dim3(nt, (Np + 255) / 256, nset * M), 256, 0, st>>>(nullptr, c.gK, ck.XK, nullptr,
-                                                                                     ck.d_ids_all, Np);
+        trmv_upper_norm_kernel<<<dim3(nt, nset * M), 256, 0, st>>>(nullptr, c.gK, ck.XK, nullptr, ck.d_ids_all, Np);
         LAUNCH_CHECK(h);
     }
     if (!init_given) {
@@ -413,7 +414,6 @@ static int run_chunk(gprn_handle* h, Chunk& ck, bool init_given, int max_iter, c
     for (int it = 0; it < iter_cap && !act.empty(); it++) {
         const int na = (int)act.size();
         CU(cudaMemsetAsync(c.logdetA, 0, sizeof(double) * (size_t)nset * M, st));
-        CU(cudaMemsetAsync(c.uv, 0, sizeof(double) * 2 * ck.vec_elems, st));   // uv and gv are adjacent
         // node phase
         prep_nodes_kernel<<<dim3(q, na), 256, 0, st>>>(c, ck.d_sets);
         LAUNCH_CHECK(h);
@@ -699,7 +699,6 @@ extern "C" int gprn_predict(gprn_handle* h, const double* hyper, const double* m
     LAUNCH_CHECK(h);
     CU(cudaMemsetAsync(c.logdetA, 0, sizeof(double) * M, st));
     CU(cudaMemsetAsync(c.mstatus, 0, sizeof(int) * M, st));
-    CU(cudaMemsetAsync(c.uv, 0, sizeof(double) * 2 * ck.vec_elems, st));
     form_a_kernel<<<dim3(ntri, M), 256, 0, st>>>(ck.W, ck.K, c.Dv, ck.d_ids_all, Np);       // + diag(v), _gp.py:125
     LAUNCH_CHECK(h);
     if (factor_batch(h, ck.W, ck.d_ids_all, M, c.logdetA, c.mstatus, ck.X, st)) return 1;

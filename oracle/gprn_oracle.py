@@ -312,18 +312,9 @@ def prediction(m: Model, tstar, mu, var, mean_at_tstar=None):
 # synthetic workloads (SURVEY.md section 8d / Appendix B generator)
 # --------------------------------------------------------------------------------------
 def synth(N, p, q, seed=1, node="QP"):
-    rng = np.random.default_rng(seed)
-    t = np.sort(rng.uniform(0, 4 * N ** 0.5 * 10, N))
-    ys, es = [], []
-    for i in range(p):
-        ys.append(np.sin(2 * np.pi * t / 25 + i) * (1 + 0.3 * i) + 0.1 * rng.standard_normal(N))
-        es.append(rng.uniform(.05, .15, N))
-    if node == "QP":
-        nodes = [("QP", 1 + .2 * j, 60 + 5 * j, 25 + j, .7) for j in range(q)]
-    else:
-        nodes = [("M52", 1 + .2 * j, 30 + 5 * j) for j in range(q)]
-    weights = [("SE", 1 + .1 * k, 80 + k) for k in range(q * p)]
-    return Model(t, np.array(ys), np.array(es), nodes, weights, None, [0.1] * p)
+    import workloads
+    a = workloads.synth_arrays(N, p, q, seed=seed, node=node)
+    return Model(a["t"], a["y"], a["yerr"], a["nodes"], a["weights"], None, a["jitters"])
 
 
 def spec_params(spec):

@@ -141,7 +141,40 @@ def kernel_vectors():
     print("kernels: ok")
 
 
+def big_anchors():
+    """Large-N anchors (C5-size with max_iter=6, C4 with max_iter=2); minutes of CPU time.
+    Only ELBO, trace and iteration count are kept (mu/var at these sizes would bloat the repo)."""
+    for name, N, mi in (("c5_synth_2048_4_2_M52_it6", 2048, 6), ("c4_synth_4096_4_2_M52_it2", 4096, 2)):
+        t, ys, es = synth_data(N, 4)
+        nodes = [("M52", 1 + .2 * j, 30 + 5 * j) for j in range(2)]
+        weights = [("SE", 1 + .1 * k, 80 + k) for k in range(8)]
+        args = []
+        for y, e in zip(ys, es):
+            args += [y, e]
+        g = meanfield.inference(2, t, *args)
+        g.set_components([build_kernel(s) for s in nodes], [build_kernel(s) for s in weights],
+                         [meanfunc.Constant(0.0)] * 4, [0.1] * 4)
+        trace = []
+        orig = g.ELBOaux
+
+        def rec(*a, **k):
+            out = orig(*a, **k)
+            trace.append(float(out[0]))
+            return out
+
+        g.ELBOaux = rec
+        elbo, mu, var, it = g.ELBOcalc(max_iter=mi)
+        np.savez_compressed(os.path.join(HERE, "big", name + ".npz"), N=N, p=4, q=2, seed=1, node="M52",
+                            max_iter=mi, elbo=float(elbo), iters=int(it), trace=np.array(trace),
+                            mu_head=np.asarray(mu)[:, :, :16], var_head=np.asarray(var)[:, :, :16])
+        print(f"{name}: ELBO={elbo!r} iters={it}", flush=True)
+
+
 def main():
+    if "--big" in sys.argv:
+        os.makedirs(os.path.join(HERE, "big"), exist_ok=True)
+        big_anchors()
+        return
     kernel_vectors()
     # notebook data (docs/examples/one_dataset.ipynb; SURVEY.md 8c anchor -267.06958539495247, 4 it)
     from scipy.stats import norm

@@ -1,0 +1,67 @@
+"""world_size-2 gloo tests of the multi-GPU partitioning logic (the N>1 path of bench.py / distributed.py).
+The path shards independent hyper-parameter sets; the only collective is the all-gather of results."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from gpyrn_b200 import distributed as D
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_indices_cover_exactly_once():
+    for B in (1, 7, 8, 8192, 8191):
+        for W in (1, 2, 4, 8):
+            for mode in ("strided", "block"):
+                got = np.concatenate([D.shard_indices(B, W, r, mode) for r in range(W)])
+                assert sorted(got.tolist()) == list(range(B))
+                sizes = [len(D.shard_indices(B, W, r, mode)) for r in range(W)]
+                assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        D.shard_indices(8, 2, 2)
+
+
+def test_gather_single_process():
+    idx = np.array([0, 2, 4])
+    out = D.gather_results(idx, {"elbo": np.array([1.0, 2.0, 3.0])}, 5)
+    assert np.allclose(out["elbo"], [1, 0, 2, 0, 3])
+
+
+def _worker(rank, world, port, B, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    idx = D.shard_indices(B, world, rank, "strided")
+    vals = {"elbo": -1000.0 - idx.astype(float), "iters": (idx % 7 + 4).astype(np.int64)}
+    out = D.gather_results(idx, vals, B)
+    ok = np.allclose(out["elbo"], -1000.0 - np.arange(B)) and np.array_equal(out["iters"], np.arange(B) % 7 + 4)
+
+    class Fake:   # stands in for an inference bound to this rank's GPU
+        def ELBO_batch(self, P, max_iter=None, return_info=False):
+            e = P.sum(axis=1)
+            return e, np.full(len(e), 5, np.int32), np.zeros(len(e), np.int32)
+
+    P = np.arange(B * 3, dtype=float).reshape(B, 3)
+    e, it, st = D.elbo_batch_sharded(Fake(), P, mode="block")
+    ok = ok and np.allclose(e, P.sum(axis=1)) and np.all(it == 5) and np.all(st == 0)
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [5, 64])
+def test_gloo_world2_gather(B):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 1000) + B
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, B, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -1,0 +1,289 @@
+"""GPU parity tests: the CUDA path, called through the Python mirror of the reference API (ctypes ->
+C ABI), against (a) golden vectors produced by the unmodified reference, (b) the CPU oracle on the
+same seeded inputs, (c) size-independent properties at the full BASELINE sizes.
+
+Bars (north_star): ELBO 1e-10 relative with identical iteration count; predictive mean / variance
+1e-8 relative; kernel matrices 1e-13 relative (FP64 exp/sin/pow within a few ulp of numpy's).
+"""
+import ast
+import os
+
+import numpy as np
+import pytest
+
+import gpyrn_b200 as gp
+from gpyrn_b200 import _lib, covfunc, meanfunc
+from oracle import gprn_oracle as orc
+from tests._cases import GOLDEN, golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+KCLS = {"SE": covfunc.SquaredExponential, "P": covfunc.Periodic, "QP": covfunc.QuasiPeriodic,
+        "RQ": covfunc.RationalQuadratic, "M32": covfunc.Matern32, "M52": covfunc.Matern52,
+        "WN": covfunc.WhiteNoise}
+
+
+def build_kernel(spec):
+    if spec[0] == "sum":
+        return build_kernel(spec[1]) + build_kernel(spec[2])
+    if spec[0] == "mul":
+        return build_kernel(spec[1]) * build_kernel(spec[2])
+    return KCLS[spec[0]](*spec[1:])
+
+
+def inference_from(t, ys, es, nodes, weights, mean_consts, jitters):
+    args = []
+    for y, e in zip(ys, es):
+        args += [y, e]
+    g = gp.inference(len(nodes), t, *args)
+    g.set_components([build_kernel(s) for s in nodes], [build_kernel(s) for s in weights],
+                     [meanfunc.Constant(c) for c in mean_consts], list(jitters))
+    return g
+
+
+def from_golden(d):
+    return inference_from(d["t"], d["y"], d["yerr"], d["nodes"], d["weights"], d["mean_consts"], d["jitters"])
+
+
+def from_oracle_model(m):
+    return inference_from(m.time, m.y, m.yerr, m.nodes, m.weights, m.mean_vals[:, 0], m.jitters)
+
+
+def full_parameters(m, theta):
+    """oracle hyper vector [kernel pars, jitters] -> get_parameters order [kernel pars, means(=const), jitters]."""
+    theta = np.atleast_2d(theta)
+    return np.concatenate([theta[:, :-m.p], np.tile(m.mean_vals[:, 0], (theta.shape[0], 1)), theta[:, -m.p:]], axis=1)
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(b)))
+
+
+# ---------------------------------------------------------------------------------------------
+# a1 / a2: kernels and covariance-matrix assembly
+# ---------------------------------------------------------------------------------------------
+def test_kernel_matrices_match_reference():
+    z = np.load(os.path.join(GOLDEN, "kernels.npz"))
+    t, ts = z["t"], z["tstar"]
+    g = gp.inference(1, t, np.zeros_like(t), np.ones_like(t))
+    for i, s in enumerate(z["specs"]):
+        k = build_kernel(ast.literal_eval(str(s)))
+        np.testing.assert_allclose(g._kmat(k, t, None, 0.0), z[f"Ksq_{i}"], rtol=1e-13, atol=1e-300)
+        np.testing.assert_allclose(g._predictKMatrix(k, ts), z[f"Krect_{i}"], rtol=1e-13, atol=1e-300)
+        np.testing.assert_allclose(k(t[:, None] - t[None, :]), z[f"Ksq_{i}"], rtol=1e-13, atol=1e-300)
+        np.testing.assert_allclose(g._KMatrix(k), z[f"Ksq_{i}"] + 1e-6 * np.eye(t.size), rtol=1e-13, atol=1e-300)
+
+
+def test_QP_equals_prod():
+    """reference tests/test_cov_functions.py:7-14"""
+    k1 = covfunc.SquaredExponential(1, 10) * covfunc.Periodic(1, 20, 0.5)
+    k2 = covfunc.QuasiPeriodic(1, 10, 20, 0.5)
+    t = np.sort(np.random.uniform(0, 100, size=50))
+    T = t[:, None] - t[None, :]
+    assert np.allclose(k1(T), k2(T))
+
+
+def test_whitenoise_shape_quirk():
+    """covfunc.py:144-148: identity by position for square input, constant otherwise (Q9)."""
+    k = covfunc.WhiteNoise(0.5)
+    assert np.allclose(k(np.ones((4, 4))), 0.25 * np.eye(4))
+    assert np.allclose(k(np.zeros((3, 4))), 0.25)
+    assert np.allclose(k(np.zeros(5)), 0.25)
+
+
+@pytest.mark.parametrize("n", [1, 17, 64, 65, 200, 500])
+def test_factorisation_kernels(n):
+    rng = np.random.default_rng(n)
+    tt = np.sort(rng.uniform(0, 40 * n ** 0.5 + 1, n))
+    A = orc.kmatrix(("M52", 1.0, 30.0), tt, nugget=1e-6) + np.diag(rng.uniform(0.01, 1.0, n))
+    g = gp.inference(1, np.arange(4.0), np.zeros(4), np.ones(4))
+    L, X, ld = np.empty((n, n)), np.empty((n, n)), np.zeros(1)
+    _lib.check(_lib.lib().gprn_debug_factor(g._h(), n, _lib.dptr(_lib.f64(A)), _lib.dptr(L), _lib.dptr(X), _lib.dptr(ld)))
+    Lr = np.linalg.cholesky(A)
+    assert rel(L, Lr) < 1e-11
+    assert np.max(np.abs(X @ Lr - np.eye(n))) < 1e-9
+    assert abs(ld[0] - 2 * np.sum(np.log(np.diag(Lr)))) <= 1e-12 * max(1.0, abs(ld[0]))
+    with pytest.raises(_lib.GprnError):
+        B = -np.eye(n)
+        _lib.check(_lib.lib().gprn_debug_factor(g._h(), n, _lib.dptr(_lib.f64(B)), _lib.dptr(L), None, None))
+
+
+# ---------------------------------------------------------------------------------------------
+# a5-a12: ELBO against the reference golden vectors
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_elbo_matches_reference(name):
+    d = load_golden(name)
+    g = from_golden(d)
+    elbo, mu, var, it = g.ELBOcalc(max_iter=d["max_iter"])
+    assert it == d["iters"]
+    assert abs(elbo - d["elbo"]) <= 1e-10 * abs(d["elbo"]), (elbo, d["elbo"])
+    assert mu.shape == var.shape == (1 + g.p, g.q, g.N)
+    assert rel(mu, d["mu"]) < 1e-8 and rel(var, d["var"]) < 1e-8
+    # converged result is cached for mu='previous' and for prediction (meanfield.py:644-645)
+    assert g._mu is mu and g._var is var
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n != "c3_synth_256_4_1_QP"])
+def test_prediction_matches_reference(name):
+    d = load_golden(name)
+    g = from_golden(d)
+    pm, pv, sep = g._Prediction(tstar=d["tstar"], mu=d["mu"], var=d["var"], separate=True)
+    assert pm.shape == pv.shape == (d["tstar"].size, g.p)
+    assert rel(pm, d["pred_mean"]) < 1e-8 and rel(pv, d["pred_var"]) < 1e-8
+    assert rel(sep[0], d["node_pred"]) < 1e-8 and rel(sep[1], d["weight_pred"]) < 1e-8
+    pm2, pv2 = g._Prediction(tstar=d["tstar"], mu=d["mu"], var=d["var"])
+    assert np.array_equal(pm, pm2) and np.array_equal(pv, pv2)
+
+
+@pytest.mark.parametrize("name", ["c5_synth_2048_4_2_M52_it6", "c4_synth_4096_4_2_M52_it2"])
+def test_large_n_anchor(name):
+    """C4 / C5-size anchors: the reference capped at max_iter (minutes of CPU time, generated once)."""
+    path = os.path.join(GOLDEN, "big", name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("large-N anchor not generated")
+    z = np.load(path)
+    m = orc.synth(int(z["N"]), int(z["p"]), int(z["q"]), seed=1, node="M52")
+    g = from_oracle_model(m)
+    elbo, mu, var, it = g.ELBOcalc(max_iter=int(z["max_iter"]))
+    assert it == int(z["iters"])
+    assert abs(elbo - float(z["elbo"])) <= 1e-10 * abs(float(z["elbo"])), (elbo, float(z["elbo"]))
+    assert rel(mu[:, :, :16], z["mu_head"]) < 1e-8 and rel(var[:, :, :16], z["var_head"]) < 1e-8
+
+
+# ---------------------------------------------------------------------------------------------
+# API behaviour of the loop
+# ---------------------------------------------------------------------------------------------
+def test_reference_smoke_elbo_property():
+    """reference tests/test_inference.py:39-53: unseeded random data, jitter 0.0, just has to run."""
+    t, y, yerr = np.random.rand(3, 10)
+    g = gp.inference(1, t, y, yerr)
+    g.set_components(covfunc.SquaredExponential(1, 1), covfunc.SquaredExponential(1, 1), meanfunc.Constant(0), 0.0)
+    assert np.isfinite(g.ELBO)
+
+
+def test_max_iter_semantics_and_init(capsys):
+    d = load_golden("synth_100_4_1_QP")
+    g = from_golden(d)
+    m = orc.Model(d["t"], d["y"], d["yerr"], d["nodes"], d["weights"], None, d["jitters"])
+    mu0, var0 = orc.init_mu_var(m)
+    mu_d, var_d = g._initMuVar(g.nodes, g.weights, g.jitters)
+    assert rel(mu_d, mu0) < 1e-15 and rel(var_d, var0) < 1e-15
+    for cap in (0, 1, 3):
+        e_o, mu_o, var_o, it_o = orc.elbo_calc(m, max_iter=cap)
+        e_g, mu_g, var_g, it_g = g.ELBOcalc(max_iter=cap)
+        assert it_g == it_o == cap
+        assert abs(e_g - e_o) <= 1e-10 * abs(e_o)
+        assert rel(mu_g.ravel(), np.asarray(mu_o).ravel()) < 1e-9
+        assert 'Max iterations reached' in capsys.readouterr().out
+    assert g._mu is None          # not cached unless converged (meanfield.py:648-649)
+    # explicit initial state == 'previous' semantics: continuing from iteration 3 reproduces iterations 4..
+    e3, mu3, var3, _ = g.ELBOcalc(max_iter=3)
+    e_g, _, _, it_g = g.ELBOcalc(mu=mu3, var=var3, max_iter=1)
+    e_o, *_ = orc.elbo_calc(m, max_iter=4)
+    assert abs(e_g - e_o) <= 1e-10 * abs(e_o)
+    one = g.ELBOaux(mu=mu3, var=var3)
+    assert abs(one[0] - e_o) <= 1e-10 * abs(e_o) and one[3] is None
+
+
+def test_previous_warm_start_and_nelbo(capsys):
+    d = load_golden("synth_100_4_1_QP")
+    g = from_golden(d)
+    e1, mu1, var1, it1 = g.ELBOcalc()
+    e2, _, _, it2 = g.ELBOcalc(mu='previous', var='previous')
+    assert it2 <= it1
+    m = orc.Model(d["t"], d["y"], d["yerr"], d["nodes"], d["weights"], None, d["jitters"])
+    e_o, *_ , it_o = orc.elbo_calc(m, mu=mu1, var=var1)
+    assert it2 == it_o and abs(e2 - e_o) <= 1e-10 * abs(e_o)
+    val = g.nELBO(g.get_parameters())
+    assert np.isfinite(val) and 'ELBO=' in capsys.readouterr().out
+    with pytest.raises(ValueError):
+        g.ELBOcalc(mu='bogus', var='bogus')
+
+
+def test_not_positive_definite_reports_nan():
+    t = np.linspace(0, 1, 20)
+    y, e = np.sin(t), np.full(20, 0.1)
+    g = gp.inference(1, t, y, e)
+    # negative-definite "kernel": theta^2 * exp(..) is fine, so break it with a huge periodic sum cancelling
+    g.set_components(covfunc.WhiteNoise(0.0), covfunc.SquaredExponential(1, 1), meanfunc.Constant(0), 0.1)
+    # K_node = 0*I + 1e-6 I is PD; make A = K + D not PD by a NaN jitter instead
+    g.jitters = np.array([np.nan])
+    elbo, mu, var, it = g.ELBOcalc()
+    assert np.isnan(elbo) and it <= 1
+
+
+# ---------------------------------------------------------------------------------------------
+# batched evaluation (ELBO_batch) against the oracle on seeded inputs, and properties at full size
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(64, 2, 1, "QP", 12), (100, 3, 2, "M52", 6), (130, 1, 1, "QP", 8)])
+def test_batch_matches_oracle(shape):
+    N, p, q, node, B = shape
+    m = orc.synth(N, p, q, seed=3, node=node)
+    theta = orc.perturbed_hyper_sets(m, B, 11)
+    g = from_oracle_model(m)
+    elbo, iters, status = g.ELBO_batch(full_parameters(m, theta), return_info=True)
+    assert elbo.shape == (B,)
+    for b in range(B):
+        try:
+            e, _, _, it = orc.elbo_calc(orc.model_with_hyper(m, theta[b]))
+        except np.linalg.LinAlgError:
+            continue                       # reference's explicit-Sigma algebra lost positive definiteness
+        if not np.isfinite(e):
+            continue
+        assert status[b] == 0 and iters[b] == it
+        assert abs(elbo[b] - e) <= 1e-10 * abs(e), (b, elbo[b], e)
+
+
+def test_batch_with_per_set_means():
+    m = orc.synth(64, 2, 1, seed=4, node="QP")
+    g = inference_from(m.time, m.y, m.yerr, m.nodes, m.weights, [0.0, 0.0], m.jitters)
+    base = g.get_parameters()
+    P = np.tile(base, (3, 1))
+    P[1, -4:-2] = [0.3, -0.2]          # mean constants of set 1
+    P[2, 0] *= 1.1
+    elbo = g.ELBO_batch(P)
+    for b in range(3):
+        nk = P.shape[1] - 4
+        mb = orc.model_with_hyper(m, np.r_[P[b, :nk], P[b, -2:]])
+        mb.mean_vals = np.repeat(P[b, nk:nk + 2][:, None], m.N, axis=1)
+        e, *_ = orc.elbo_calc(mb)
+        assert abs(elbo[b] - e) <= 1e-10 * abs(e)
+
+
+def test_c3_full_size_properties():
+    """C3 (N=256, p=4, q=1) at a large batch: every set is independent, so the batch result must equal the
+    single evaluation bit for bit, be invariant under permutation of the sets, and reproduce the
+    reference anchor for theta_0."""
+    m = orc.synth(256, 4, 1, seed=1, node="QP")
+    B = 1024
+    theta = orc.perturbed_hyper_sets(m, B, 101)
+    theta[0] = orc.perturbed_hyper_sets(m, 1, 0)[0] * 0 + np.r_[sum((orc.spec_params(s) for s in m.nodes + m.weights), []), m.jitters]
+    g = from_oracle_model(m)
+    P = full_parameters(m, theta)
+    elbo, iters, status = g.ELBO_batch(P, return_info=True)
+    d = load_golden("c3_synth_256_4_1_QP")
+    assert iters[0] == d["iters"] and abs(elbo[0] - d["elbo"]) <= 1e-10 * abs(d["elbo"])
+    assert np.all(status == 0) and np.all(np.isfinite(elbo)) and iters.min() >= 4
+    perm = np.random.default_rng(0).permutation(B)
+    elbo_p, iters_p, _ = g.ELBO_batch(P[perm], return_info=True)
+    assert np.array_equal(elbo_p, elbo[perm]) and np.array_equal(iters_p, iters[perm])
+    for b in (1, 17, 1023):
+        g.set_parameters(P[b])
+        e1, _, _, it1 = g.ELBOcalc()
+        assert e1 == elbo[b] and it1 == iters[b]
+    # oracle spot check on a few perturbed sets
+    for b in (1, 2, 3):
+        e, _, _, it = orc.elbo_calc(orc.model_with_hyper(m, theta[b]))
+        assert iters[b] == it and abs(elbo[b] - e) <= 1e-10 * abs(e)
+
+
+def test_workspace_chunking_is_transparent():
+    m = orc.synth(128, 2, 1, seed=2, node="QP")
+    theta = orc.perturbed_hyper_sets(m, 40, 5)
+    g = from_oracle_model(m)
+    P = full_parameters(m, theta)
+    ref = g.ELBO_batch(P)
+    _lib.check(_lib.lib().gprn_set_workspace_limit(g._h(), 7 * 3 * 3 * 128 * 128 * 8 + (1 << 20)))   # ~7 sets per chunk
+    got = g.ELBO_batch(P)
+    assert np.array_equal(ref, got)

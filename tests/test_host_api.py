@@ -1,0 +1,199 @@
+"""CPU tests of the host side: the reference's own API tests (tests/test_inference.py:8-36,
+tests/test_mean_functions.py:7-35, tests/test_imports.py) re-stated against gpyrn_b200, the
+parameter bookkeeping (meanfield.py:180-379), kernel-program serialisation, and the C ABI
+surface (library loads and exports every symbol include/gprn_b200.h declares).  No compute calls."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gpyrn_b200
+from gpyrn_b200 import _lib, covfunc, meanfunc
+from gpyrn_b200.meanfield import inference
+from gpyrn_b200.meanfunc import Constant, Linear
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_imports():
+    assert gpyrn_b200.inference is inference
+    assert gpyrn_b200.SquaredExponential is covfunc.SquaredExponential
+    assert gpyrn_b200.QuasiPeriodic is covfunc.QuasiPeriodic
+    assert gpyrn_b200.Constant is meanfunc.Constant and gpyrn_b200.Linear is meanfunc.Linear
+
+
+def test_create_inference():
+    t, y, yerr = np.random.rand(3, 10)
+    gprn = inference(1, t, y, yerr)
+    assert gprn.time is t
+    assert gprn.N == t.size and gprn.q == 1 and gprn.p == 1
+    t, y1, ye1, y2, ye2 = np.random.rand(5, 10)
+    gprn = inference(1, t, y1, ye1, y2, ye2)
+    assert np.allclose(gprn.y, np.c_[y1, y2].T)
+    assert np.allclose(gprn.yerr2, np.c_[ye1, ye2].T ** 2)
+    assert gprn.q == 1 and gprn.p == 2 and gprn.qp == 2 and gprn.d == 10 * 1 * 3
+
+
+def test_create_inference_exception():
+    with pytest.raises(TypeError):
+        _ = inference(1)
+    with pytest.raises(AssertionError):
+        _ = inference(1, np.random.rand(10))
+    t, y1, ye1 = np.random.rand(3, 10)
+    y2, ye2 = np.random.rand(2, 20)
+    with pytest.raises(AssertionError):
+        _ = inference(1, t, y1, ye1, y2, ye2)
+
+
+def test_set_components_forms_and_errors():
+    t, y, yerr = np.random.rand(3, 10)
+    gprn = inference(1, t, y, yerr)
+    node, weight = covfunc.SquaredExponential(1, 1), covfunc.SquaredExponential(1, 1)
+    mean = meanfunc.Constant(0)
+    gprn.set_components(node, weight, mean, 0.0)
+    assert gprn.nodes[0] is node
+    gprn.set_components([node], [weight], mean, 0.0)
+    gprn.set_components([node], [weight], [mean], [0.0])
+    assert gprn.jitters.dtype == float
+    with pytest.raises(ValueError):
+        gprn.set_components([node, node], [weight], [mean], [0.0])
+    with pytest.raises(ValueError):
+        gprn.set_components([node], [weight, weight], [mean], [0.0])
+    with pytest.raises(ValueError):
+        inference(1, t, y, yerr).get_parameters()
+
+
+def _two_output():
+    t = np.linspace(0, 10, 12)
+    y1, e1, y2, e2 = np.random.rand(4, 12)
+    g = inference(2, t, y1, e1, y2, e2)
+    nodes = [covfunc.QuasiPeriodic(1, 2, 3, 4), covfunc.Matern52(5, 6)]
+    weights = [covfunc.SquaredExponential(7 + k, 20 + k) for k in range(4)]
+    g.set_components(nodes, weights, [meanfunc.Constant(0.5), meanfunc.Linear(0.1, 0.2)], [0.3, 0.4])
+    return g
+
+
+def test_parameter_vector_order_names_and_freezing():
+    g = _two_output()
+    assert g.n_parameters == 4 + 2 + 8 + 1 + 2 + 2
+    expected = [1, 2, 3, 4, 5, 6, 7, 20, 8, 21, 9, 22, 10, 23, 0.5, 0.1, 0.2, 0.3, 0.4]
+    assert np.allclose(g.get_parameters(), expected)
+    names = list(g.parameters_dict.keys())
+    assert names[:6] == ['node1.theta', 'node1.le', 'node1.P', 'node1.lp', 'node2.theta', 'node2.ell']
+    assert names[6:8] == ['weight1.theta', 'weight1.ell'] and names[-2:] == ['jitter1', 'jitter2']
+    assert names[14:17] == ['mean1.c', 'mean2.slope', 'mean2.intercept']
+    new = np.arange(19, dtype=float) + 100
+    g.set_parameters(new)
+    assert np.allclose(g.get_parameters(), new)
+    assert np.allclose(g.nodes[1].pars, [104, 105]) and np.allclose(g.jitters, [117, 118])
+    g.freeze_parameter(name='node1*')
+    assert g.frozen_mask.sum() == 4 and g.get_parameters().size == 15
+    g.set_parameters(np.zeros(15) + 7)
+    assert np.allclose(g.nodes[0].pars, [100, 101, 102, 103]) and np.allclose(g.nodes[1].pars, 7)
+    g.thaw_parameter(name='node1.P')
+    assert g.frozen_mask.sum() == 3
+    g.freeze_parameter(index=18)
+    assert g.frozen_mask[18]
+    g.thaw_all_parameters()
+    assert g.frozen_mask.sum() == 0
+    with pytest.raises(ValueError):
+        g.set_parameters(np.zeros(3))
+    with pytest.raises(NotImplementedError):
+        g.frozen_mask = np.zeros(19, bool)
+    with pytest.raises(AssertionError):
+        g.freeze_parameter(name='nope')
+
+
+def test_kernel_programs_and_composition():
+    se, per = covfunc.SquaredExponential(1, 10), covfunc.Periodic(1, 20, 0.5)
+    k = se * per + covfunc.WhiteNoise(0.1)
+    assert k.program() == [covfunc.OP_SE, covfunc.OP_PER, covfunc.OP_MUL, covfunc.OP_WN, covfunc.OP_ADD]
+    assert np.allclose(k.pars, [1, 10, 1, 20, 0.5, 0.1])
+    rest = k.set_parameters(np.arange(8.0))
+    assert np.allclose(rest, [6, 7])
+    assert np.allclose(se.pars, [0, 1]) and np.allclose(per.pars, [2, 3, 4])      # operands follow the composite
+    assert covfunc.QuasiPeriodic(1, 2, 3, 4)._param_names == ('theta', 'le', 'P', 'lp')
+    assert covfunc.Matern32(1, 2)._tag == 'M32' and covfunc.RationalQuadratic(1, 2, 3)._tag == 'RQ'
+    assert 'theta=1.0' in repr(covfunc.Matern52(1, 2))
+    assert covfunc.SquaredExponential(1, 2).set_parameters([3, 4]) is None
+    with pytest.raises(AssertionError):
+        covfunc.SquaredExponential(1, 2).set_parameters([3])
+
+
+def test_Constant():
+    m = Constant(0.0)
+    assert m.pars[0] == 0.0 and np.all(m(np.random.rand(10)) == 0.0)
+    m = Constant(10.0)
+    assert m.pars[0] == 10.0 and np.all(m(np.random.rand(3)) == 10.0)
+    with pytest.raises(TypeError):
+        m = Constant()
+    assert np.all((Constant(5.0) + Constant(10.0))(np.random.rand(3)) == 15.0)
+    assert np.all((Constant(2) * Constant(10.0))(np.random.rand(3)) == 20.0)
+    assert (Constant(5.0) + Constant(10.0))._param_names == ('c1', 'c2')
+
+
+def test_Linear_and_polynomials():
+    m = Linear(0.0, 1.0)
+    assert m.pars[0] == 0.0 and m.pars[1] == 1.0 and np.all(m(np.random.rand(10)) == 1.0)
+    m = Linear(1.0, 2.0)
+    t = np.array([0.0, 1.0, 2.0, 3.0])
+    assert np.all(m(t) == np.polyval(m.pars, t - t.mean()))
+    assert np.allclose(meanfunc.Parabola(1, 2, 3)(t), t ** 2 + 2 * t + 3)
+    assert np.allclose(meanfunc.Cubic(1, 0, 0, 1)(t), t ** 3 + 1)
+    assert np.allclose(meanfunc.Sine(2, 4, 0.5)(t), 2 * np.sin(2 * np.pi * t / 4 + 0.5))
+    s = Linear(1.0, 2.0) + meanfunc.Sine(1, 2, 3)
+    assert s.set_parameters(np.arange(6.0)) .tolist() == [5.0]
+    assert np.allclose(s.m2.pars, [2, 3, 4])
+
+
+def test_MultiConstant():
+    t = np.arange(6.0)
+    obs = np.array([1, 1, 1, 2, 2, 2])
+    m = meanfunc.MultiConstant([1.5, 10.0], obs, t)
+    assert np.allclose(m(t), [11.5, 11.5, 11.5, 10, 10, 10])
+    assert m._param_names == ['off1', 'mean']
+
+
+def test_mean_vector_host():
+    t = np.linspace(0, 1, 5)
+    y1, e1, y2, e2 = np.random.rand(4, 5)
+    g = inference(1, t, y1, e1, y2, e2)
+    mv = g._mean([Constant(2.0), None])
+    assert np.allclose(mv, np.r_[np.full(5, 2.0), np.zeros(5)])
+    f, w = g._u_to_fhatW(np.arange(g.d, dtype=float))
+    assert f.shape == (1, 1, 5) and w.shape == (2, 1, 5)
+
+
+def test_cabi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "gprn_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(gprn_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    L = _lib.lib()                       # loads without a GPU (no CUDA call at load time)
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/gprn_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert L.gprn_built_for_sm() == 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without a CUDA device the product must raise, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    t, y, yerr = np.random.rand(3, 10)
+    g = inference(1, t, y, yerr)
+    g.set_components(covfunc.SquaredExponential(1, 1), covfunc.SquaredExponential(1, 1), Constant(0), 0.1)
+    with pytest.raises(_lib.GprnError):
+        _ = g.ELBO
+    with pytest.raises(_lib.GprnError):
+        covfunc.SquaredExponential(1, 1)(np.zeros((3, 3)))
+
+
+def test_product_does_not_import_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "gpyrn_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert "oracle" not in src, f"{f} mentions the oracle"
