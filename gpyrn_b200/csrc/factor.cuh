@@ -12,6 +12,7 @@
 // cho_solve (:1032-1051) and scipy cho_factor/cho_solve (gpyrn/_gp.py:126-135).
 #pragma once
 #include "common.cuh"
+#include "gemm128.cuh"
 
 namespace gprn {
 
@@ -214,6 +215,178 @@ __global__ void __launch_bounds__(128) trtri_row_kernel(double* __restrict__ X, 
     for (int e = tid; e < NB * NB; e += 128) {
         int m = e >> 6, n = e & 63;
         Xt[(size_t)m * Np + n] = V[m * LDV + n];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Large-N path (Np a multiple of 256): two-level blocking.  Panels of 256 columns are factored with the
+// 64-tile kernels above (syrk restricted to the panel's own columns); the trailing matrix is then updated
+// once per panel with 128x128 tiles and a K = 256 deep DMMA product (gemm128.cuh).
+// ------------------------------------------------------------------------------------------------
+#define OUTER_KB 256
+
+// In-panel trailing update after tile column k: A_ij -= L_ik L_jk^T for J in (k, jend), I in [J, nt).
+// grid = ((nt-k-1) * (jend-k-1), nmat), block = 128.
+__global__ void __launch_bounds__(128) syrk_inpanel_kernel(double* __restrict__ W, const int* __restrict__ ids, int Np,
+                                                           int k, int jend) {
+    extern __shared__ double smem[];
+    double* As = smem;
+    double* Bs = smem + NB * LDT;
+    const int ncols = jend - k - 1;
+    const int I = k + 1 + blockIdx.x / ncols, J = k + 1 + blockIdx.x % ncols;
+    if (J > I) return;
+    const int id = ids[blockIdx.y];
+    double* Wm = W + (size_t)id * Np * Np;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 1, wn = warp & 1;
+    load_tile<false>(As, Wm + (size_t)(I * NB) * Np + k * NB, Np, tid, 128);
+    if (I != J) load_tile<false>(Bs, Wm + (size_t)(J * NB) * Np + k * NB, Np, tid, 128);
+    const double* Bp = (I != J) ? Bs : As;
+    double* C = Wm + (size_t)(I * NB) * Np + J * NB;
+    double acc[4][4][2];
+    const int r = lane >> 2, c = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double2 v = *reinterpret_cast<const double2*>(C + (size_t)(wm * 32 + i * 8 + r) * Np + wn * 32 + j * 8 + 2 * c);
+            acc[i][j][0] = v.x;
+            acc[i][j][1] = v.y;
+        }
+    __syncthreads();
+    mma_tile<true>(acc, As, Bp, wm, wn, lane);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+            *reinterpret_cast<double2*>(C + (size_t)(wm * 32 + i * 8 + r) * Np + wn * 32 + j * 8 + 2 * c) = v;
+        }
+}
+
+// Trailing update after the 256-column panel starting at column c0: for 128x128 tiles (TI >= TJ) of the
+// trailing square starting at t0 = c0 + 256:  C -= L[rows, c0:c0+256] L[cols, c0:c0+256]^T.
+// grid = (n(n+1)/2 with n = (Np - t0)/128, nmat), block = 256, dynamic smem GEMM128_SMEM.
+__global__ void __launch_bounds__(256) syrk_outer_kernel(double* __restrict__ W, const int* __restrict__ ids, int Np,
+                                                         int c0) {
+    extern __shared__ double smem[];
+    int TI, TJ;
+    tri_decode(blockIdx.x, TI, TJ);
+    const int t0 = c0 + OUTER_KB;
+    const int r0 = t0 + TI * G_BM, n0 = t0 + TJ * G_BN;
+    const int id = ids[blockIdx.y];
+    double* Wm = W + (size_t)id * Np * Np;
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    gemm128_mainloop<false>(acc, smem, Wm + (size_t)r0 * Np + c0, Np, Wm + (size_t)n0 * Np + c0, Np, OUTER_KB);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3;
+    const int r = lane >> 2, c = lane & 3;
+    double* C = Wm + (size_t)r0 * Np + n0;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double2* p = reinterpret_cast<double2*>(C + (size_t)(wm * 64 + i * 8 + r) * Np + wn * 32 + j * 8 + 2 * c);
+            double2 v = *p;
+            v.x -= acc[i][j][0];
+            v.y -= acc[i][j][1];
+            *p = v;
+        }
+}
+
+// Inverse, block row of 256 rows starting at R0: X[rows, 0:R0] = - L[rows, n0:R0] X[n0:R0, cols] (the part of
+// the row-sweep sum that lies above the block), 128x128 tiles.  X must hold zeros in its upper tiles.
+// grid = (2 * R0/128, nmat), block = 256, dynamic smem GEMM128_SMEM.
+__global__ void __launch_bounds__(256) trtri_outer_kernel(double* __restrict__ X, const double* __restrict__ W,
+                                                          const int* __restrict__ ids, int Np, int R0) {
+    extern __shared__ double smem[];
+    const int ncol = R0 / G_BN;
+    const int TJ = blockIdx.x % ncol, half = blockIdx.x / ncol;
+    const int r0 = R0 + half * G_BM, n0 = TJ * G_BN;
+    const int id = ids[blockIdx.y];
+    const double* Wm = W + (size_t)id * Np * Np;
+    double* Xm = X + (size_t)id * Np * Np;
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    gemm128_mainloop<true>(acc, smem, Wm + (size_t)r0 * Np + n0, Np, Xm + (size_t)n0 * Np + n0, Np, R0 - n0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3;
+    const int r = lane >> 2, c = lane & 3;
+    double* C = Xm + (size_t)r0 * Np + n0;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double2 v = make_double2(-acc[i][j][0], -acc[i][j][1]);
+            *reinterpret_cast<double2*>(C + (size_t)(wm * 64 + i * 8 + r) * Np + wn * 32 + j * 8 + 2 * c) = v;
+        }
+}
+
+// Inverse, in-block sweep for the 4 tile rows i = i0 .. i0+3 of a 256-row block: one CTA per 64-column tile j
+// walks the rows in order,  X_ij = L_ii^-1 ( G'_ij - sum_{k=max(j,i0)}^{i-1} L_ik X_kj ),  with G' the partial
+// sum left in place by trtri_outer_kernel (zero for columns inside the block).  grid = (i0 + 3, nmat),
+// block = 128, dynamic smem TRTRI_SMEM.
+__global__ void __launch_bounds__(128) trtri_inblock_kernel(double* __restrict__ X, const double* __restrict__ W,
+                                                            const int* __restrict__ ids, int Np, int i0) {
+    extern __shared__ double smem[];
+    double* As = smem;
+    double* Bs = smem + NB * LDT;
+    double* V = smem + 2 * NB * LDT;
+    const int id = ids[blockIdx.y], j = blockIdx.x;
+    const double* Wm = W + (size_t)id * Np * Np;
+    double* Xm = X + (size_t)id * Np * Np;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int r = lane >> 2, c = lane & 3;
+    const int kstart = max(j, i0);
+    for (int i = max(i0, j + 1); i < i0 + 4; i++) {
+        double acc[4][4][2];
+        double* Xt = Xm + (size_t)(i * NB) * Np + j * NB;
+        if (j < i0) {
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    double2 v = *reinterpret_cast<const double2*>(Xt + (size_t)(wm * 32 + a * 8 + r) * Np + wn * 32 + b * 8 + 2 * c);
+                    acc[a][b][0] = v.x;
+                    acc[a][b][1] = v.y;
+                }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+        }
+        for (int k = kstart; k < i; k++) {
+            load_tile<false>(As, Wm + (size_t)(i * NB) * Np + k * NB, Np, tid, 128);
+            load_tile<true>(Bs, Xm + (size_t)(k * NB) * Np + j * NB, Np, tid, 128);
+            __syncthreads();
+            mma_tile<true>(acc, As, Bs, wm, wn, lane);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                int m = wm * 32 + a * 8 + r, n = wn * 32 + b * 8 + 2 * c;
+                V[m * LDV + n] = acc[a][b][0];
+                V[m * LDV + n + 1] = acc[a][b][1];
+            }
+        load_tile<false>(As, Wm + (size_t)(i * NB) * Np + i * NB, Np, tid, 128);
+        __syncthreads();
+        if (tid < NB) subst_lower(As, LDT, V, LDV, tid);
+        __syncthreads();
+        for (int e = tid; e < NB * NB; e += 128) {
+            int m = e >> 6, n = e & 63;
+            Xt[(size_t)m * Np + n] = V[m * LDV + n];
+        }
+        __threadfence_block();
+        __syncthreads();     // X_ij is read back (as a B operand) by this CTA for the next rows
     }
 }
 

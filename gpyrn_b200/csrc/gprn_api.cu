@@ -77,6 +77,14 @@ static int ensure(DevBuf& b, size_t bytes) {
     b.bytes = bytes;
     return 0;
 }
+static int ensure_zeroed(DevBuf& b, size_t bytes) {
+    if (b.bytes >= bytes) return 0;
+    if (ensure(b, bytes)) return 1;
+    cudaError_t e = cudaMemset(b.p, 0, b.bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return fail(std::string("cudaMemset: ") + cudaGetErrorString(e));
+    return 0;
+}
 static int ensure_pinned(int*& p, size_t& n, size_t want) {
     if (n >= want) return 0;
     if (p) cudaFreeHost(p);
@@ -88,6 +96,13 @@ static int ensure_pinned(int*& p, size_t& n, size_t want) {
     return 0;
 }
 
+// Padded matrix order: multiples of 64; beyond 1024 multiples of 256 so that the two-level (large-N) path applies.
+static int padded_size(int n) {
+    const int unit = n > 1024 ? OUTER_KB : NB;
+    return ((n + unit - 1) / unit) * unit;
+}
+static bool use_two_level(int Np) { return Np >= 512 && Np % OUTER_KB == 0 && getenv("GPRN_NO_TWO_LEVEL") == nullptr; }
+
 static bool g_attr_done = false;
 static int set_kernel_attrs() {
     if (g_attr_done) return 0;
@@ -95,6 +110,10 @@ static int set_kernel_attrs() {
     CU(cudaFuncSetAttribute(syrk_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(trtri_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
     CU(cudaFuncSetAttribute(trtri_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_DIAG_SMEM));
+    CU(cudaFuncSetAttribute(syrk_inpanel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
+    CU(cudaFuncSetAttribute(syrk_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM128_SMEM));
+    CU(cudaFuncSetAttribute(trtri_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM128_SMEM));
+    CU(cudaFuncSetAttribute(trtri_inblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
     CU(cudaFuncSetAttribute(cross_frob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(predict_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     g_attr_done = true;
@@ -122,7 +141,7 @@ extern "C" int gprn_create(int device, int N, int p, int q, const double* time, 
     gprn_handle* h = new gprn_handle();
     h->device = device;
     h->N = N;
-    h->Np = ((N + NB - 1) / NB) * NB;
+    h->Np = padded_size(N);
     h->nt = h->Np / NB;
     h->p = p;
     h->q = q;
@@ -252,6 +271,45 @@ extern "C" int gprn_set_model(gprn_handle* h, const int32_t* node_prog, const in
 static int factor_batch(gprn_handle* h, double* W, const int* d_ids, int nmat, double* logdet, int* mstatus,
                         double* X /* null: no inverse */, cudaStream_t st) {
     const int nt = h->nt, Np = h->Np;
+    if (use_two_level(Np)) {
+        const int nb = Np / OUTER_KB;
+        for (int ko = 0; ko < nb; ko++) {
+            const int jend = 4 * ko + 4;
+            for (int k = 4 * ko; k < jend; k++) {
+                potrf_diag_kernel<<<nmat, 256, 0, st>>>(W, d_ids, Np, k, logdet, mstatus);
+                LAUNCH_CHECK(h);
+                const int n = nt - k - 1;
+                if (n > 0) {
+                    trsm_panel_kernel<<<dim3((n + 1) / 2, nmat), 128, TRSM_SMEM, st>>>(W, d_ids, Np, k);
+                    LAUNCH_CHECK(h);
+                }
+                const int ncols = jend - k - 1;
+                if (ncols > 0) {
+                    syrk_inpanel_kernel<<<dim3(n * ncols, nmat), 128, 2 * TILE_SMEM, st>>>(W, d_ids, Np, k, jend);
+                    LAUNCH_CHECK(h);
+                }
+            }
+            const int n128 = (Np - (ko + 1) * OUTER_KB) / G_BM;
+            if (n128 > 0) {
+                syrk_outer_kernel<<<dim3(n128 * (n128 + 1) / 2, nmat), 256, GEMM128_SMEM, st>>>(W, d_ids, Np, ko * OUTER_KB);
+                LAUNCH_CHECK(h);
+            }
+        }
+        if (X) {
+            trtri_diag_kernel<<<dim3(nt, nmat), 64, TRTRI_DIAG_SMEM, st>>>(X, W, d_ids, Np);
+            LAUNCH_CHECK(h);
+            for (int I = 0; I < nb; I++) {
+                const int R0 = I * OUTER_KB;
+                if (R0 > 0) {
+                    trtri_outer_kernel<<<dim3(2 * (R0 / G_BN), nmat), 256, GEMM128_SMEM, st>>>(X, W, d_ids, Np, R0);
+                    LAUNCH_CHECK(h);
+                }
+                trtri_inblock_kernel<<<dim3(4 * I + 3, nmat), 128, TRTRI_SMEM, st>>>(X, W, d_ids, Np, 4 * I);
+                LAUNCH_CHECK(h);
+            }
+        }
+        return 0;
+    }
     for (int k = 0; k < nt; k++) {
         potrf_diag_kernel<<<nmat, 256, 0, st>>>(W, d_ids, Np, k, logdet, mstatus);
         LAUNCH_CHECK(h);
@@ -306,8 +364,10 @@ static size_t per_set_bytes(const gprn_handle* h) {
 static int setup_chunk(gprn_handle* h, int nset, Chunk& ck, bool ysub_per_set) {
     const size_t Np = h->Np, M = h->M;
     const size_t matbytes = (size_t)nset * M * Np * Np * sizeof(double);
-    if (ensure(h->K, matbytes) || ensure(h->W, matbytes) || ensure(h->X, matbytes)) return 1;
-    if (h->q > 1 && ensure(h->XK, matbytes)) return 1;
+    if (ensure(h->K, matbytes) || ensure(h->W, matbytes)) return 1;
+    // the inverse factors must hold zeros in their (never written) upper tiles: trtri_outer_kernel reads them
+    if (ensure_zeroed(h->X, matbytes)) return 1;
+    if (h->q > 1 && ensure_zeroed(h->XK, matbytes)) return 1;
     const size_t ve = (size_t)nset * M * Np;
     if (ensure(h->vecs, 7 * ve * sizeof(double))) return 1;
     if (ensure(h->state, 4 * (size_t)nset * h->d * sizeof(double))) return 1;
@@ -620,7 +680,7 @@ extern "C" int gprn_debug_factor(gprn_handle* h, int n, const double* A, double*
     if (!h || !A || n < 1) return fail("gprn_debug_factor: bad argument");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = h->own_stream;
-    const int Np = ((n + NB - 1) / NB) * NB;
+    const int Np = padded_size(n);
     std::vector<double> pad((size_t)Np * Np, 0.0);
     for (int i = 0; i < Np; i++) pad[(size_t)i * Np + i] = 1.0;
     for (int i = 0; i < n; i++)
