@@ -78,12 +78,15 @@ __device__ __forceinline__ void mma_tile(double (&acc)[4][4][2], const double* _
 
 // Forward substitution  L y = g  for ONE vector per thread, everything in shared memory.
 //   Ls : 64x64 lower-triangular tile, element (m,k) at Ls[m*lds + k]   (read by broadcast)
+//   rd : reciprocals of the diagonal of Ls (64 values)
 //   V  : vectors, element m of vector n at V[m*ldv + n]
 //   first_block : rows below first_block*8 are known to be zero on input (identity right-hand sides)
-// Blocked by 8 so that the 8 running values stay in registers; divisions (not reciprocal
-// multiplications) as in LAPACK dtrsm -- see DESIGN.md "Numerics" for why this matters here.
-__device__ __forceinline__ void subst_lower(const double* __restrict__ Ls, int lds, double* __restrict__ V,
-                                            int ldv, int n, int first_block = 0) {
+// Blocked by 8 so that the 8 running values stay in registers.  This is a genuine substitution (LAPACK
+// dtrsm semantics) -- multiplying by an explicit inverse of the tile instead costs 1-2 digits of ELBO
+// parity on these ill-conditioned matrices (DESIGN.md "Numerics"); only the 64 scalar divisions by the
+// diagonal are replaced by multiplications with its reciprocal (<= 1 ulp each, off the critical path).
+__device__ __forceinline__ void subst_lower(const double* __restrict__ Ls, int lds, const double* __restrict__ rd,
+                                            double* __restrict__ V, int ldv, int n, int first_block = 0) {
     for (int mb = first_block; mb < 8; mb++) {
         double y[8];
 #pragma unroll
@@ -104,11 +107,62 @@ __device__ __forceinline__ void subst_lower(const double* __restrict__ Ls, int l
             const double* lrow = Ls + (mb * 8 + u) * lds + mb * 8;
 #pragma unroll
             for (int w = 0; w < u; w++) y[u] = fma(-lrow[w], y[w], y[u]);
-            y[u] = y[u] / lrow[u];
+            y[u] = y[u] * rd[mb * 8 + u];
         }
 #pragma unroll
         for (int u = 0; u < 8; u++) V[(mb * 8 + u) * ldv + n] = y[u];
     }
+}
+
+// Cholesky of a 64x64 tile by 256 threads with the tile held in registers (thread (r, q4) owns row r,
+// columns q4 + 4u).  Outer-product form on UNSCALED columns (T[r][c] = L[r][c] * L[c][c], pivot = L[c][c]^2),
+// so a step needs one barrier: the owners of column c+1 publish it to shared memory as soon as step c has
+// updated it.  Scaling by 1/sqrt(pivot) happens once at the end.
+//   Td  : input tile in shared memory, element (m,n) at Td[m*ldd + n] (lower triangle used)
+//   Ls  : output, lower-triangular L with zeros above the diagonal, stride LDT (may alias Td)
+//   rd  : output, 1 / L[c][c];   col: scratch 128 doubles;   pivs: scratch 64 doubles (pivots L[c][c]^2)
+//   bad : set to 1 when a pivot is not positive (caller zeroes it)
+__device__ __forceinline__ void potrf64(const double* Td, int ldd, double* Ls, double* __restrict__ rd,
+                                        double* __restrict__ col, double* __restrict__ pivs, int* bad) {
+    const int tid = threadIdx.x, r = tid >> 2, q4 = tid & 3;
+    double a[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) a[u] = Td[r * ldd + q4 + 4 * u];
+    if (q4 == 0) col[r] = a[0];
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < NB; c++) {
+        const double* cb = col + (c & 1) * NB;
+        const double piv = cb[c];
+        if (tid == 0) {
+            pivs[c] = piv;
+            if (!(piv > 0.0)) *bad = 1;
+        }
+        if (r > c) {
+            const double t = cb[r] * (1.0 / piv);
+#pragma unroll
+            for (int u = c >> 2; u < 16; u++) {
+                const int cc = q4 + 4 * u;
+                if (cc > c && cc <= r) a[u] = fma(-t, cb[cc], a[u]);
+            }
+        }
+        if (c + 1 < NB) {
+            if (q4 == ((c + 1) & 3)) col[((c + 1) & 1) * NB + r] = a[(c + 1) >> 2];
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    if (tid < NB) rd[tid] = 1.0 / sqrt(pivs[tid]);
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+        const int cc = q4 + 4 * u;
+        double v = 0.0;
+        if (cc < r) v = a[u] * rd[cc];
+        else if (cc == r) v = sqrt(pivs[r]);
+        Ls[r * LDT + cc] = v;
+    }
+    __syncthreads();
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

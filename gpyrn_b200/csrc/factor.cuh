@@ -38,100 +38,122 @@ __global__ void __launch_bounds__(256) form_a_kernel(double* __restrict__ W, con
     }
 }
 
-// Cholesky of diagonal tile k of every listed matrix; accumulates 2*sum(log diag) into logdet[id]
-// and raises status[id] when a pivot is not positive.  grid = (nmat), block = 256.
-__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ W, const int* __restrict__ ids, int Np,
-                                                         int k, double* __restrict__ logdet,
-                                                         int* __restrict__ status) {
-    __shared__ double T[NB * LDV];
-    __shared__ int bad;
-    const int id = ids[blockIdx.x];
-    double* A = W + (size_t)id * Np * Np + (size_t)(k * NB) * Np + k * NB;
-    const int tid = threadIdx.x;
-    if (tid == 0) bad = 0;
-    for (int e = tid; e < NB * NB; e += 256) {
-        int r = e >> 6, c = e & 63;
-        T[r * LDV + c] = A[(size_t)r * Np + c];
-    }
-    __syncthreads();
-    for (int c = 0; c < NB; c++) {
-        if (tid == 0) {
-            double piv = T[c * LDV + c];
-            if (!(piv > 0.0)) bad = 1;
-            T[c * LDV + c] = sqrt(piv);
-        }
-        __syncthreads();
-        const double d = T[c * LDV + c];
-        if (tid > c && tid < NB) T[tid * LDV + c] = T[tid * LDV + c] / d;
-        __syncthreads();
-        for (int e = (c + 1) * NB + tid; e < NB * NB; e += 256) {
-            int r = e >> 6, cc = e & 63;
-            if (cc > c && cc <= r) T[r * LDV + cc] = fma(-T[r * LDV + c], T[cc * LDV + c], T[r * LDV + cc]);
-        }
-        __syncthreads();
-    }
-    for (int e = tid; e < NB * NB; e += 256) {
-        int r = e >> 6, c = e & 63;
-        A[(size_t)r * Np + c] = (c <= r) ? T[r * LDV + c] : 0.0;
-    }
-    if (tid < 32) {
-        double s = log(T[tid * LDV + tid]) + log(T[(tid + 32) * LDV + tid + 32]);
-        s = warp_sum(s);
-        if (tid == 0) {
-            atomicAdd(&logdet[id], 2.0 * s);
-            if (bad) status[id] = 1;
-        }
-    }
-}
-
-// Panel solve below diagonal tile k: rows of tiles i = k+1+2*blockIdx.x (+1).  grid = (ceil((nt-k-1)/2), nmat),
-// block = 128 (one matrix row per thread).  Shared memory: Ls[64*LDT] + V[64*129].
+// Left-looking panel step for tile column k of the panel that starts at tile column k0 (panels are 4 tile
+// columns wide): every CTA (a) forms A_kk - sum_{k'} L_kk' L_kk'^T over the panel's finished columns and
+// factors it (redundantly -- it is 64^3/3 flops and saves a launch plus a grid-wide dependency), (b) does the
+// same update for its own two row tiles i0, i0+1 and solves them against L_kk.  L_kk overwrites A_kk, which
+// every CTA of the matrix reads, so it is stored by whichever CTA is the LAST to have consumed A_kk (ticket in
+// ctr[id], self-resetting; no spinning); that CTA also adds sum(log pivots) = 2 sum(log diag L) to logdet[id]
+// and raises status[id] on a non-positive pivot.
+// grid = (max(1, ceil((nt-k-1)/2)), nmat), block = 256 (warps 0-3: diagonal + row tile i0, warps 4-7: i0+1).
+#define PANEL_SMEM ((3 * NB * LDT + 4 * NB) * sizeof(double))
 #define TRSM_LDV 129
-#define TRSM_SMEM ((NB * LDT + NB * TRSM_LDV) * sizeof(double))
-__global__ void __launch_bounds__(128) trsm_panel_kernel(double* __restrict__ W, const int* __restrict__ ids, int Np,
-                                                         int k) {
+__global__ void __launch_bounds__(256) panel_col_kernel(double* __restrict__ W, const int* __restrict__ ids, int Np,
+                                                        int k, int k0, double* __restrict__ logdet,
+                                                        int* __restrict__ status, int* __restrict__ ctr) {
     extern __shared__ double smem[];
-    double* Ls = smem;
-    double* V = smem + NB * LDT;
-    const int id = ids[blockIdx.y];
+    double* Bs = smem;                 // L_kk' operand; then potrf input (stride LDV) and output L_kk (stride LDT)
+    double* As0 = smem + NB * LDT;     // L_i0k' / L_i1k' operands; then V (substitution vectors, stride 129)
+    double* As1 = smem + 2 * NB * LDT;
+    double* V = As0;
+    double* col = smem + 3 * NB * LDT;
+    double* pivs = col + 2 * NB;
+    double* rd = pivs + NB;
+    __shared__ int bad, last;
     const int nt = Np / NB;
+    const int id = ids[blockIdx.y];
     double* Wm = W + (size_t)id * Np * Np;
-    const int row0 = (k + 1 + 2 * blockIdx.x) * NB;
-    const int nrows = min(2 * NB, Np - row0);
-    const int tid = threadIdx.x;
-    (void)nt;
-    load_tile<false>(Ls, Wm + (size_t)(k * NB) * Np + k * NB, Np, tid, 128);
-    // A rows -> V[c][r] (vector index = row)
-    for (int e = tid; e < nrows * NB; e += 128) {
-        int r = e >> 6, c = e & 63;
-        V[c * TRSM_LDV + r] = Wm[(size_t)(row0 + r) * Np + k * NB + c];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = warp >> 2, w4 = warp & 3, wm = w4 >> 1, wn = w4 & 1, tid4 = tid & 127;
+    const int r = lane >> 2, c = lane & 3;
+    const int i_own = k + 1 + 2 * blockIdx.x + grp;
+    const bool has = i_own < nt;
+    if (tid == 0) bad = 0;
+    double accd[4][4][2], accr[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int m = wm * 32 + a * 8 + r, n = wn * 32 + b * 8 + 2 * c;
+            accd[a][b][0] = accd[a][b][1] = accr[a][b][0] = accr[a][b][1] = 0.0;
+            if (grp == 0) {
+                double2 v = *reinterpret_cast<const double2*>(Wm + (size_t)(k * NB + m) * Np + k * NB + n);
+                accd[a][b][0] = v.x; accd[a][b][1] = v.y;
+            }
+            if (has) {
+                double2 v = *reinterpret_cast<const double2*>(Wm + (size_t)(i_own * NB + m) * Np + k * NB + n);
+                accr[a][b][0] = v.x; accr[a][b][1] = v.y;
+            }
+        }
+    for (int kp = k0; kp < k; kp++) {
+        load_tile<false>(Bs, Wm + (size_t)(k * NB) * Np + kp * NB, Np, tid, 256);
+        if (has) load_tile<false>(grp ? As1 : As0, Wm + (size_t)(i_own * NB) * Np + kp * NB, Np, tid4, 128);
+        __syncthreads();
+        if (grp == 0) mma_tile<true>(accd, Bs, Bs, wm, wn, lane);
+        if (has) mma_tile<true>(accr, grp ? As1 : As0, Bs, wm, wn, lane);
+        __syncthreads();
     }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int m = wm * 32 + a * 8 + r, n = wn * 32 + b * 8 + 2 * c;
+            if (grp == 0) {
+                Bs[m * LDV + n] = accd[a][b][0];
+                Bs[m * LDV + n + 1] = accd[a][b][1];
+            }
+            if (has) {
+                V[n * TRSM_LDV + grp * NB + m] = accr[a][b][0];
+                V[(n + 1) * TRSM_LDV + grp * NB + m] = accr[a][b][1];
+            }
+        }
     __syncthreads();
-    if (tid < nrows) subst_lower(Ls, LDT, V, TRSM_LDV, tid);
+    if (tid == 0) {      // every value of A_kk this CTA needs now sits in shared memory
+        const int prev = atomicAdd(&ctr[id], 1);
+        last = (prev == (int)gridDim.x - 1);
+        if (last) ctr[id] = 0;
+    }
+    potrf64(Bs, LDV, Bs, rd, col, pivs, &bad);
+    if (tid < 2 * NB && (k + 1 + 2 * (int)blockIdx.x + (tid >> 6)) < nt) subst_lower(Bs, LDT, rd, V, TRSM_LDV, tid);
     __syncthreads();
-    for (int e = tid; e < nrows * NB; e += 128) {
-        int r = e >> 6, c = e & 63;
-        Wm[(size_t)(row0 + r) * Np + k * NB + c] = V[c * TRSM_LDV + r];
+    if (has) {
+        double* dst = Wm + (size_t)(i_own * NB) * Np + k * NB;
+        for (int e = tid4; e < NB * NB; e += 128) {
+            int m = e >> 6, n = e & 63;
+            dst[(size_t)m * Np + n] = V[n * TRSM_LDV + grp * NB + m];
+        }
+    }
+    if (last) {
+        double* dst = Wm + (size_t)(k * NB) * Np + k * NB;
+        for (int e = tid; e < NB * NB; e += 256) {
+            int m = e >> 6, n = e & 63;
+            dst[(size_t)m * Np + n] = Bs[m * LDT + n];
+        }
+        if (tid < 32) {
+            double sl = log(pivs[tid]) + log(pivs[tid + 32]);
+            sl = warp_sum(sl);
+            if (tid == 0) {
+                atomicAdd(&logdet[id], sl);
+                if (bad) status[id] = 1;
+            }
+        }
     }
 }
 
-// Trailing update after panel k: A_ij -= L_ik L_jk^T for k < j <= i.  grid = (n(n+1)/2 with n = nt-k-1, nmat),
-// block = 128 (2x2 warps, 32x32 each).  Dynamic shared memory 2*TILE_SMEM.
+// Trailing update after tile columns [kb, ke): A_ij -= sum_{k=kb}^{ke-1} L_ik L_jk^T for ke <= j <= i (64x64 tiles).
+// grid = (n(n+1)/2 with n = nt-ke, nmat), block = 128 (2x2 warps, 32x32 each).  Dynamic shared memory 2*TILE_SMEM.
 __global__ void __launch_bounds__(128) syrk_update_kernel(double* __restrict__ W, const int* __restrict__ ids, int Np,
-                                                          int k) {
+                                                          int kb, int ke) {
     extern __shared__ double smem[];
     double* As = smem;
     double* Bs = smem + NB * LDT;
     int ti, tj;
     tri_decode(blockIdx.x, ti, tj);
-    const int I = k + 1 + ti, J = k + 1 + tj;
+    const int I = ke + ti, J = ke + tj;
     const int id = ids[blockIdx.y];
     double* Wm = W + (size_t)id * Np * Np;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wm = warp >> 1, wn = warp & 1;
-    load_tile<false>(As, Wm + (size_t)(I * NB) * Np + k * NB, Np, tid, 128);
-    if (I != J) load_tile<false>(Bs, Wm + (size_t)(J * NB) * Np + k * NB, Np, tid, 128);
-    const double* Bp = (I != J) ? Bs : As;
     double* C = Wm + (size_t)(I * NB) * Np + J * NB;
     double acc[4][4][2];
     const int r = lane >> 2, c = lane & 3;
@@ -143,8 +165,13 @@ __global__ void __launch_bounds__(128) syrk_update_kernel(double* __restrict__ W
             acc[i][j][0] = v.x;
             acc[i][j][1] = v.y;
         }
-    __syncthreads();
-    mma_tile<true>(acc, As, Bp, wm, wn, lane);
+    for (int k = kb; k < ke; k++) {
+        load_tile<false>(As, Wm + (size_t)(I * NB) * Np + k * NB, Np, tid, 128);
+        if (I != J) load_tile<false>(Bs, Wm + (size_t)(J * NB) * Np + k * NB, Np, tid, 128);
+        __syncthreads();
+        mma_tile<true>(acc, As, (I != J) ? Bs : As, wm, wn, lane);
+        __syncthreads();
+    }
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -155,7 +182,7 @@ __global__ void __launch_bounds__(128) syrk_update_kernel(double* __restrict__ W
 }
 
 // X_ii = L_ii^-1 for every diagonal tile.  grid = (nt, nmat), block = 64 (one column per thread).
-#define TRTRI_DIAG_SMEM ((NB * LDT + NB * LDV) * sizeof(double))
+#define TRTRI_DIAG_SMEM ((NB * LDT + NB * LDV + NB) * sizeof(double))
 __global__ void __launch_bounds__(64) trtri_diag_kernel(double* __restrict__ X, const double* __restrict__ W,
                                                         const int* __restrict__ ids, int Np) {
     extern __shared__ double smem[];
@@ -163,10 +190,13 @@ __global__ void __launch_bounds__(64) trtri_diag_kernel(double* __restrict__ X, 
     double* V = smem + NB * LDT;
     const int id = ids[blockIdx.y], i = blockIdx.x, tid = threadIdx.x;
     const size_t off = (size_t)id * Np * Np + (size_t)(i * NB) * Np + i * NB;
+    double* rd = V + NB * LDV;
     load_tile<false>(Ls, W + off, Np, tid, 64);
     for (int m = 0; m < NB; m++) V[m * LDV + tid] = (m == tid) ? 1.0 : 0.0;
     __syncthreads();
-    subst_lower(Ls, LDT, V, LDV, tid, tid >> 3);
+    rd[tid] = 1.0 / Ls[tid * LDT + tid];
+    __syncthreads();
+    subst_lower(Ls, LDT, rd, V, LDV, tid, tid >> 3);
     __syncthreads();
     double* Xt = X + off;
     for (int m = 0; m < NB; m++) Xt[(size_t)m * Np + tid] = V[m * LDV + tid];
@@ -174,7 +204,7 @@ __global__ void __launch_bounds__(64) trtri_diag_kernel(double* __restrict__ X, 
 
 // Block row i of the inverse: X_ij for j = blockIdx.x < i.  grid = (i, nmat), block = 128.
 // Dynamic shared memory: As, Bs (MMA operands) + V (64*LDV).
-#define TRTRI_SMEM (2 * TILE_SMEM + NB * LDV * sizeof(double))
+#define TRTRI_SMEM (2 * TILE_SMEM + (NB * LDV + NB) * sizeof(double))
 __global__ void __launch_bounds__(128) trtri_row_kernel(double* __restrict__ X, const double* __restrict__ W,
                                                         const int* __restrict__ ids, int Np, int i) {
     extern __shared__ double smem[];
@@ -209,7 +239,10 @@ __global__ void __launch_bounds__(128) trtri_row_kernel(double* __restrict__ X, 
         }
     load_tile<false>(As, Wm + (size_t)(i * NB) * Np + i * NB, Np, tid, 128);        // L_ii
     __syncthreads();
-    if (tid < NB) subst_lower(As, LDT, V, LDV, tid);
+    double* rd = V + NB * LDV;
+    if (tid < NB) rd[tid] = 1.0 / As[tid * LDT + tid];
+    __syncthreads();
+    if (tid < NB) subst_lower(As, LDT, rd, V, LDV, tid);
     __syncthreads();
     double* Xt = Xm + (size_t)(i * NB) * Np + j * NB;
     for (int e = tid; e < NB * NB; e += 128) {
@@ -224,45 +257,6 @@ __global__ void __launch_bounds__(128) trtri_row_kernel(double* __restrict__ X, 
 // once per panel with 128x128 tiles and a K = 256 deep DMMA product (gemm128.cuh).
 // ------------------------------------------------------------------------------------------------
 #define OUTER_KB 256
-
-// In-panel trailing update after tile column k: A_ij -= L_ik L_jk^T for J in (k, jend), I in [J, nt).
-// grid = ((nt-k-1) * (jend-k-1), nmat), block = 128.
-__global__ void __launch_bounds__(128) syrk_inpanel_kernel(double* __restrict__ W, const int* __restrict__ ids, int Np,
-                                                           int k, int jend) {
-    extern __shared__ double smem[];
-    double* As = smem;
-    double* Bs = smem + NB * LDT;
-    const int ncols = jend - k - 1;
-    const int I = k + 1 + blockIdx.x / ncols, J = k + 1 + blockIdx.x % ncols;
-    if (J > I) return;
-    const int id = ids[blockIdx.y];
-    double* Wm = W + (size_t)id * Np * Np;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wm = warp >> 1, wn = warp & 1;
-    load_tile<false>(As, Wm + (size_t)(I * NB) * Np + k * NB, Np, tid, 128);
-    if (I != J) load_tile<false>(Bs, Wm + (size_t)(J * NB) * Np + k * NB, Np, tid, 128);
-    const double* Bp = (I != J) ? Bs : As;
-    double* C = Wm + (size_t)(I * NB) * Np + J * NB;
-    double acc[4][4][2];
-    const int r = lane >> 2, c = lane & 3;
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            double2 v = *reinterpret_cast<const double2*>(C + (size_t)(wm * 32 + i * 8 + r) * Np + wn * 32 + j * 8 + 2 * c);
-            acc[i][j][0] = v.x;
-            acc[i][j][1] = v.y;
-        }
-    __syncthreads();
-    mma_tile<true>(acc, As, Bp, wm, wn, lane);
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
-            *reinterpret_cast<double2*>(C + (size_t)(wm * 32 + i * 8 + r) * Np + wn * 32 + j * 8 + 2 * c) = v;
-        }
-}
 
 // Trailing update after the 256-column panel starting at column c0: for 128x128 tiles (TI >= TJ) of the
 // trailing square starting at t0 = c0 + 256:  C -= L[rows, c0:c0+256] L[cols, c0:c0+256]^T.
@@ -329,7 +323,7 @@ __global__ void __launch_bounds__(256) trtri_outer_kernel(double* __restrict__ X
 
 // Inverse, in-block sweep for the 4 tile rows i = i0 .. i0+3 of a 256-row block: one CTA per 64-column tile j
 // walks the rows in order,  X_ij = L_ii^-1 ( G'_ij - sum_{k=max(j,i0)}^{i-1} L_ik X_kj ),  with G' the partial
-// sum left in place by trtri_outer_kernel (zero for columns inside the block).  grid = (i0 + 3, nmat),
+// sum left in place by trtri_outer_kernel (zero for columns inside the block).  grid = (min(i0+4, nt) - 1, nmat),
 // block = 128, dynamic smem TRTRI_SMEM.
 __global__ void __launch_bounds__(128) trtri_inblock_kernel(double* __restrict__ X, const double* __restrict__ W,
                                                             const int* __restrict__ ids, int Np, int i0) {
@@ -344,7 +338,8 @@ __global__ void __launch_bounds__(128) trtri_inblock_kernel(double* __restrict__
     const int wm = warp >> 1, wn = warp & 1;
     const int r = lane >> 2, c = lane & 3;
     const int kstart = max(j, i0);
-    for (int i = max(i0, j + 1); i < i0 + 4; i++) {
+    const int iend = min(i0 + 4, Np / NB);
+    for (int i = max(i0, j + 1); i < iend; i++) {
         double acc[4][4][2];
         double* Xt = Xm + (size_t)(i * NB) * Np + j * NB;
         if (j < i0) {
@@ -379,7 +374,10 @@ __global__ void __launch_bounds__(128) trtri_inblock_kernel(double* __restrict__
             }
         load_tile<false>(As, Wm + (size_t)(i * NB) * Np + i * NB, Np, tid, 128);
         __syncthreads();
-        if (tid < NB) subst_lower(As, LDT, V, LDV, tid);
+        double* rd = V + NB * LDV;
+        if (tid < NB) rd[tid] = 1.0 / As[tid * LDT + tid];
+        __syncthreads();
+        if (tid < NB) subst_lower(As, LDT, rd, V, LDV, tid);
         __syncthreads();
         for (int e = tid; e < NB * NB; e += 128) {
             int m = e >> 6, n = e & 63;

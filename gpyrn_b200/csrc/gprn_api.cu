@@ -106,11 +106,10 @@ static bool use_two_level(int Np) { return Np >= 512 && Np % OUTER_KB == 0 && ge
 static bool g_attr_done = false;
 static int set_kernel_attrs() {
     if (g_attr_done) return 0;
-    CU(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM));
+    CU(cudaFuncSetAttribute(panel_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
     CU(cudaFuncSetAttribute(syrk_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(trtri_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
     CU(cudaFuncSetAttribute(trtri_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_DIAG_SMEM));
-    CU(cudaFuncSetAttribute(syrk_inpanel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(syrk_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM128_SMEM));
     CU(cudaFuncSetAttribute(trtri_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM128_SMEM));
     CU(cudaFuncSetAttribute(trtri_inblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
@@ -269,64 +268,49 @@ extern "C" int gprn_set_model(gprn_handle* h, const int32_t* node_prog, const in
 // batched factorisation driver
 // ------------------------------------------------------------------------------------------------
 static int factor_batch(gprn_handle* h, double* W, const int* d_ids, int nmat, double* logdet, int* mstatus,
-                        double* X /* null: no inverse */, cudaStream_t st) {
+                        int* ctr /* per-matrix tickets, zero between launches */, double* X /* null: no inverse */,
+                        cudaStream_t st) {
     const int nt = h->nt, Np = h->Np;
-    if (use_two_level(Np)) {
-        const int nb = Np / OUTER_KB;
-        for (int ko = 0; ko < nb; ko++) {
-            const int jend = 4 * ko + 4;
-            for (int k = 4 * ko; k < jend; k++) {
-                potrf_diag_kernel<<<nmat, 256, 0, st>>>(W, d_ids, Np, k, logdet, mstatus);
-                LAUNCH_CHECK(h);
-                const int n = nt - k - 1;
-                if (n > 0) {
-                    trsm_panel_kernel<<<dim3((n + 1) / 2, nmat), 128, TRSM_SMEM, st>>>(W, d_ids, Np, k);
-                    LAUNCH_CHECK(h);
-                }
-                const int ncols = jend - k - 1;
-                if (ncols > 0) {
-                    syrk_inpanel_kernel<<<dim3(n * ncols, nmat), 128, 2 * TILE_SMEM, st>>>(W, d_ids, Np, k, jend);
-                    LAUNCH_CHECK(h);
-                }
-            }
-            const int n128 = (Np - (ko + 1) * OUTER_KB) / G_BM;
-            if (n128 > 0) {
-                syrk_outer_kernel<<<dim3(n128 * (n128 + 1) / 2, nmat), 256, GEMM128_SMEM, st>>>(W, d_ids, Np, ko * OUTER_KB);
-                LAUNCH_CHECK(h);
-            }
-        }
-        if (X) {
-            trtri_diag_kernel<<<dim3(nt, nmat), 64, TRTRI_DIAG_SMEM, st>>>(X, W, d_ids, Np);
+    const bool two = use_two_level(Np);
+    // Cholesky: panels of 4 tile columns, left-looking inside the panel, right-looking trailing update per panel
+    for (int k0 = 0; k0 < nt; k0 += 4) {
+        const int ke = std::min(k0 + 4, nt);
+        for (int k = k0; k < ke; k++) {
+            const int n = nt - k - 1;
+            panel_col_kernel<<<dim3(std::max(1, (n + 1) / 2), nmat), 256, PANEL_SMEM, st>>>(W, d_ids, Np, k, k0, logdet, mstatus, ctr);
             LAUNCH_CHECK(h);
-            for (int I = 0; I < nb; I++) {
-                const int R0 = I * OUTER_KB;
-                if (R0 > 0) {
-                    trtri_outer_kernel<<<dim3(2 * (R0 / G_BN), nmat), 256, GEMM128_SMEM, st>>>(X, W, d_ids, Np, R0);
-                    LAUNCH_CHECK(h);
-                }
-                trtri_inblock_kernel<<<dim3(4 * I + 3, nmat), 128, TRTRI_SMEM, st>>>(X, W, d_ids, Np, 4 * I);
-                LAUNCH_CHECK(h);
-            }
         }
-        return 0;
-    }
-    for (int k = 0; k < nt; k++) {
-        potrf_diag_kernel<<<nmat, 256, 0, st>>>(W, d_ids, Np, k, logdet, mstatus);
-        LAUNCH_CHECK(h);
-        const int n = nt - k - 1;
-        if (n > 0) {
-            trsm_panel_kernel<<<dim3((n + 1) / 2, nmat), 128, TRSM_SMEM, st>>>(W, d_ids, Np, k);
-            LAUNCH_CHECK(h);
-            syrk_update_kernel<<<dim3(n * (n + 1) / 2, nmat), 128, 2 * TILE_SMEM, st>>>(W, d_ids, Np, k);
+        if (ke < nt) {
+            if (two) {
+                const int n128 = (Np - ke * NB) / G_BM;
+                syrk_outer_kernel<<<dim3(n128 * (n128 + 1) / 2, nmat), 256, GEMM128_SMEM, st>>>(W, d_ids, Np, k0 * NB);
+            } else {
+                const int n = nt - ke;
+                syrk_update_kernel<<<dim3(n * (n + 1) / 2, nmat), 128, 2 * TILE_SMEM, st>>>(W, d_ids, Np, k0, ke);
+            }
             LAUNCH_CHECK(h);
         }
     }
     if (X) {
         trtri_diag_kernel<<<dim3(nt, nmat), 64, TRTRI_DIAG_SMEM, st>>>(X, W, d_ids, Np);
         LAUNCH_CHECK(h);
-        for (int i = 1; i < nt; i++) {
-            trtri_row_kernel<<<dim3(i, nmat), 128, TRTRI_SMEM, st>>>(X, W, d_ids, Np, i);
-            LAUNCH_CHECK(h);
+        if (two || nt <= 4) {
+            for (int i0 = 0; i0 < nt; i0 += 4) {
+                if (i0 > 0) {
+                    trtri_outer_kernel<<<dim3(2 * (i0 * NB / G_BN), nmat), 256, GEMM128_SMEM, st>>>(X, W, d_ids, Np, i0 * NB);
+                    LAUNCH_CHECK(h);
+                }
+                const int ncol = std::min(i0 + 4, nt) - 1;
+                if (ncol > 0) {
+                    trtri_inblock_kernel<<<dim3(ncol, nmat), 128, TRTRI_SMEM, st>>>(X, W, d_ids, Np, i0);
+                    LAUNCH_CHECK(h);
+                }
+            }
+        } else {
+            for (int i = 1; i < nt; i++) {
+                trtri_row_kernel<<<dim3(i, nmat), 128, TRTRI_SMEM, st>>>(X, W, d_ids, Np, i);
+                LAUNCH_CHECK(h);
+            }
         }
     }
     return 0;
@@ -348,7 +332,7 @@ struct Chunk {
     int nset;
     ElboCtx c;
     double *K, *W, *X, *XK;
-    int *d_sets, *d_ids_nodes, *d_ids_weights, *d_ids_all;
+    int *d_sets, *d_ids_nodes, *d_ids_weights, *d_ids_all, *d_ctr;
     size_t vec_elems;
 };
 
@@ -375,8 +359,8 @@ static int setup_chunk(gprn_handle* h, int nset, Chunk& ck, bool ysub_per_set) {
     //        hist [nset*3]; elbo [nset] doubles; then ints
     const size_t ncross = (size_t)(h->q * (h->q - 1) / 2) * h->nt * h->nt;
     const size_t nd = 5 * (size_t)nset * M + (size_t)nset * (1 + ncross + 3 + 1);
-    const size_t ni = 3 * (size_t)nset + (size_t)nset * M;
-    if (ensure(h->small, nd * sizeof(double) + ni * sizeof(int))) return 1;
+    const size_t ni = 3 * (size_t)nset + 2 * (size_t)nset * M;
+    if (ensure_zeroed(h->small, nd * sizeof(double) + ni * sizeof(int))) return 1;
     const size_t nl = (size_t)nset * (1 + 2 * M);
     if (ensure(h->lists, nl * sizeof(int))) return 1;
     if (ensure_pinned(h->h_lists, h->h_lists_n, nl)) return 1;
@@ -408,6 +392,7 @@ static int setup_chunk(gprn_handle* h, int nset, Chunk& ck, bool ysub_per_set) {
     c.elbo = c.hist + (size_t)nset * 3;
     int* si = (int*)(c.elbo + nset);
     c.iters = si; c.status = si + nset; c.active = si + 2 * nset; c.mstatus = si + 3 * nset;
+    ck.d_ctr = si + 3 * nset + nm;      // tickets of panel_col_kernel: zero at allocation, self-resetting
     int* l = (int*)h->lists.p;
     ck.d_sets = l; ck.d_ids_nodes = l + nset; ck.d_ids_weights = l + nset + (size_t)nset * h->q;
     ck.d_ids_all = l + nset + (size_t)nset * M;
@@ -451,9 +436,10 @@ static int run_chunk(gprn_handle* h, Chunk& ck, bool init_given, int max_iter, c
     LAUNCH_CHECK(h);
     CU(cudaMemsetAsync(c.logdetK, 0, sizeof(double) * (size_t)nset * M, st));
     CU(cudaMemsetAsync(c.mstatus, 0, sizeof(int) * (size_t)nset * M, st));
+    CU(cudaMemsetAsync(ck.d_ctr, 0, sizeof(int) * (size_t)nset * M, st));
     form_a_kernel<<<dim3(ntri, nset * M), 256, 0, st>>>(ck.W, ck.K, nullptr, ck.d_ids_all, Np);
     LAUNCH_CHECK(h);
-    if (factor_batch(h, ck.W, ck.d_ids_all, nset * M, c.logdetK, c.mstatus, q > 1 ? ck.XK : nullptr, st)) return 1;
+    if (factor_batch(h, ck.W, ck.d_ids_all, nset * M, c.logdetK, c.mstatus, ck.d_ctr, q > 1 ? ck.XK : nullptr, st)) return 1;
     if (q > 1) {
         trmv_upper_norm_kernel<<<dim3(nt, nset * M), 256, 0, st>>>(nullptr, c.gK, ck.XK, nullptr, ck.d_ids_all, Np);
         LAUNCH_CHECK(h);
@@ -479,7 +465,7 @@ static int run_chunk(gprn_handle* h, Chunk& ck, bool init_given, int max_iter, c
         LAUNCH_CHECK(h);
         form_a_kernel<<<dim3(ntri, na * q), 256, 0, st>>>(ck.W, ck.K, c.Dv, ck.d_ids_nodes, Np);
         LAUNCH_CHECK(h);
-        if (factor_batch(h, ck.W, ck.d_ids_nodes, na * q, c.logdetA, c.mstatus, ck.X, st)) return 1;
+        if (factor_batch(h, ck.W, ck.d_ids_nodes, na * q, c.logdetA, c.mstatus, ck.d_ctr, ck.X, st)) return 1;
         if (solve_batch(h, ck.X, ck.d_ids_nodes, na * q, c.vv, c.zv, c.uv, c.gv, ck.vec_elems, st)) return 1;
         post_kernel<<<dim3(q, na), 256, 0, st>>>(c, ck.d_sets, 0, q == 1);
         LAUNCH_CHECK(h);
@@ -494,7 +480,7 @@ static int run_chunk(gprn_handle* h, Chunk& ck, bool init_given, int max_iter, c
         LAUNCH_CHECK(h);
         form_a_kernel<<<dim3(ntri, na * q * p), 256, 0, st>>>(ck.W, ck.K, c.Dv, ck.d_ids_weights, Np);
         LAUNCH_CHECK(h);
-        if (factor_batch(h, ck.W, ck.d_ids_weights, na * q * p, c.logdetA, c.mstatus, ck.X, st)) return 1;
+        if (factor_batch(h, ck.W, ck.d_ids_weights, na * q * p, c.logdetA, c.mstatus, ck.d_ctr, ck.X, st)) return 1;
         if (solve_batch(h, ck.X, ck.d_ids_weights, na * q * p, c.vv, c.zv, c.uv, c.gv, ck.vec_elems, st)) return 1;
         post_kernel<<<dim3(q * p, na), 256, 0, st>>>(c, ck.d_sets, q, q == 1);
         LAUNCH_CHECK(h);
@@ -686,22 +672,24 @@ extern "C" int gprn_debug_factor(gprn_handle* h, int n, const double* A, double*
     for (int i = 0; i < n; i++)
         for (int j = 0; j < n; j++) pad[(size_t)i * Np + j] = A[(size_t)i * n + j];
     double *dW = nullptr, *dX = nullptr, *dld = nullptr;
-    int *dids = nullptr, *dst = nullptr;
+    int *dids = nullptr, *dst = nullptr, *dctr = nullptr;
     CU(cudaMalloc(&dW, sizeof(double) * Np * Np));
     CU(cudaMalloc(&dX, sizeof(double) * Np * Np));
     CU(cudaMalloc(&dld, sizeof(double)));
     CU(cudaMalloc(&dids, sizeof(int)));
     CU(cudaMalloc(&dst, sizeof(int)));
+    CU(cudaMalloc(&dctr, sizeof(int)));
     // everything on `st`: the handle's stream is non-blocking, so legacy-stream memsets would race with it
     CU(cudaMemcpyAsync(dW, pad.data(), sizeof(double) * Np * Np, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(dX, 0, sizeof(double) * Np * Np, st));
     CU(cudaMemsetAsync(dld, 0, sizeof(double), st));
     CU(cudaMemsetAsync(dids, 0, sizeof(int), st));
     CU(cudaMemsetAsync(dst, 0, sizeof(int), st));
+    CU(cudaMemsetAsync(dctr, 0, sizeof(int), st));
     gprn_handle tmp = *h;          // borrow counters / geometry for the driver
     tmp.Np = Np;
     tmp.nt = Np / NB;
-    int rc = factor_batch(&tmp, dW, dids, 1, dld, dst, dX, st);
+    int rc = factor_batch(&tmp, dW, dids, 1, dld, dst, dctr, dX, st);
     h->launches = tmp.launches;
     tmp.all.clear();
     if (rc) return rc;
@@ -720,7 +708,7 @@ extern "C" int gprn_debug_factor(gprn_handle* h, int n, const double* A, double*
     if (logdet_out) CU(cudaMemcpy(logdet_out, dld, sizeof(double), cudaMemcpyDeviceToHost));
     int stt = 0;
     CU(cudaMemcpy(&stt, dst, sizeof(int), cudaMemcpyDeviceToHost));
-    cudaFree(dW); cudaFree(dX); cudaFree(dld); cudaFree(dids); cudaFree(dst);
+    cudaFree(dW); cudaFree(dX); cudaFree(dld); cudaFree(dids); cudaFree(dst); cudaFree(dctr);
     if (stt) return fail("gprn_debug_factor: matrix is not positive definite");
     return 0;
 }
@@ -759,9 +747,10 @@ extern "C" int gprn_predict(gprn_handle* h, const double* hyper, const double* m
     LAUNCH_CHECK(h);
     CU(cudaMemsetAsync(c.logdetA, 0, sizeof(double) * M, st));
     CU(cudaMemsetAsync(c.mstatus, 0, sizeof(int) * M, st));
+    CU(cudaMemsetAsync(ck.d_ctr, 0, sizeof(int) * M, st));
     form_a_kernel<<<dim3(ntri, M), 256, 0, st>>>(ck.W, ck.K, c.Dv, ck.d_ids_all, Np);       // + diag(v), _gp.py:125
     LAUNCH_CHECK(h);
-    if (factor_batch(h, ck.W, ck.d_ids_all, M, c.logdetA, c.mstatus, ck.X, st)) return 1;
+    if (factor_batch(h, ck.W, ck.d_ids_all, M, c.logdetA, c.mstatus, ck.d_ctr, ck.X, st)) return 1;
     if (solve_batch(h, ck.X, ck.d_ids_all, M, c.vv, c.zv, c.uv, c.gv, ck.vec_elems, st)) return 1;   // uv = alpha
     // test points in chunks
     const int TC = 4096;
