@@ -1,6 +1,6 @@
 // gemm128.cuh -- FP64 tensor-core GEMM core for the large-N path: one CTA computes a 128x128 tile of
 //     acc = sum_k A[m][k] * B(k, n)
-// on DMMA m8n8k4 with a 3-stage cp.async (LDGSTS, 16-byte) shared-memory pipeline.
+// on DMMA m8n8k4 with a multi-stage cp.async (LDGSTS, 16-byte) shared-memory pipeline.
 //   A : row-major, k contiguous ("[m][k]").
 //   B : !B_KMAJOR  row-major [n][k], k contiguous   (NT product, e.g. L_ik L_jk^T)
 //        B_KMAJOR  row-major [k][n], n contiguous   (NN product, e.g. L_ik X_kj)
@@ -16,7 +16,9 @@ namespace gprn {
 #define G_BM 128
 #define G_BN 128
 #define G_BK 16
-#define G_STAGES 3
+#ifndef G_STAGES
+#define G_STAGES 4
+#endif
 #define G_LDA 20                    // As[m][k]
 #define G_LDB_NT 20                 // Bs[n][k]
 #define G_LDB_NN 132                // Bs[k][n]

@@ -48,6 +48,9 @@ struct gprn_handle {
     bool model_set = false;
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    static const int NAUX = 4;
+    cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr, nullptr, nullptr};
     int64_t launches = 0;
     double last_ms = 0.0;
     int64_t last_total_iters = 0;
@@ -149,6 +152,11 @@ extern "C" int gprn_create(int device, int N, int p, int q, const double* time, 
     CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
+    CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (int g = 0; g < gprn_handle::NAUX; g++) {
+        CU(cudaStreamCreateWithFlags(&h->aux[g], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_join[g], cudaEventDisableTiming));
+    }
     CU(cudaMalloc(&h->d_time, sizeof(double) * h->Np));
     CU(cudaMalloc(&h->d_y, sizeof(double) * p * N));
     CU(cudaMalloc(&h->d_yerr2, sizeof(double) * p * N));
@@ -178,7 +186,8 @@ extern "C" int gprn_destroy(gprn_handle* h) {
     if (h->d_par_off) cudaFree(h->d_par_off);
     if (h->h_lists) cudaFreeHost(h->h_lists);
     if (h->h_active) cudaFreeHost(h->h_active);
-    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev_fork);
+    for (int g = 0; g < gprn_handle::NAUX; g++) { cudaStreamDestroy(h->aux[g]); cudaEventDestroy(h->ev_join[g]); }
     cudaStreamDestroy(h->own_stream);
     delete h;
     return 0;
@@ -316,6 +325,28 @@ static int factor_batch(gprn_handle* h, double* W, const int* d_ids, int nmat, d
     return 0;
 }
 
+// Large matrices: the factorisation of one matrix alternates between wide GEMM launches and narrow, latency-
+// bound panel launches.  Independent matrices are therefore split into groups that run the whole pipeline on
+// concurrent streams, so that one group's panel steps overlap another group's trailing updates.
+static int factor_batch_multi(gprn_handle* h, double* W, const int* d_ids, int nmat, double* logdet, int* mstatus,
+                              int* ctr, double* X, cudaStream_t st) {
+    static const int groups_env = getenv("GPRN_FACTOR_GROUPS") ? atoi(getenv("GPRN_FACTOR_GROUPS")) : 0;
+    int G = groups_env > 0 ? groups_env : gprn_handle::NAUX;
+    if (!use_two_level(h->Np) || nmat < 2 || G < 2) return factor_batch(h, W, d_ids, nmat, logdet, mstatus, ctr, X, st);
+    G = std::min(std::min(G, (int)gprn_handle::NAUX), nmat);
+    CU(cudaEventRecord(h->ev_fork, st));
+    int start = 0;
+    for (int g = 0; g < G; g++) {
+        const int len = nmat / G + (g < nmat % G ? 1 : 0);
+        CU(cudaStreamWaitEvent(h->aux[g], h->ev_fork, 0));
+        if (factor_batch(h, W, d_ids + start, len, logdet, mstatus, ctr, X, h->aux[g])) return 1;
+        CU(cudaEventRecord(h->ev_join[g], h->aux[g]));
+        CU(cudaStreamWaitEvent(st, h->ev_join[g], 0));
+        start += len;
+    }
+    return 0;
+}
+
 // z = X v ; u = X^T z ; g = colnorm2(X)   for the listed matrices (u, g zeroed here)
 static int solve_batch(gprn_handle* h, const double* X, const int* d_ids, int nmat, double* vv, double* zv,
                        double* uv, double* gv, size_t vec_elems, cudaStream_t st) {
@@ -439,7 +470,7 @@ static int run_chunk(gprn_handle* h, Chunk& ck, bool init_given, int max_iter, c
     CU(cudaMemsetAsync(ck.d_ctr, 0, sizeof(int) * (size_t)nset * M, st));
     form_a_kernel<<<dim3(ntri, nset * M), 256, 0, st>>>(ck.W, ck.K, nullptr, ck.d_ids_all, Np);
     LAUNCH_CHECK(h);
-    if (factor_batch(h, ck.W, ck.d_ids_all, nset * M, c.logdetK, c.mstatus, ck.d_ctr, q > 1 ? ck.XK : nullptr, st)) return 1;
+    if (factor_batch_multi(h, ck.W, ck.d_ids_all, nset * M, c.logdetK, c.mstatus, ck.d_ctr, q > 1 ? ck.XK : nullptr, st)) return 1;
     if (q > 1) {
         trmv_upper_norm_kernel<<<dim3(nt, nset * M), 256, 0, st>>>(nullptr, c.gK, ck.XK, nullptr, ck.d_ids_all, Np);
         LAUNCH_CHECK(h);
@@ -465,7 +496,7 @@ static int run_chunk(gprn_handle* h, Chunk& ck, bool init_given, int max_iter, c
         LAUNCH_CHECK(h);
         form_a_kernel<<<dim3(ntri, na * q), 256, 0, st>>>(ck.W, ck.K, c.Dv, ck.d_ids_nodes, Np);
         LAUNCH_CHECK(h);
-        if (factor_batch(h, ck.W, ck.d_ids_nodes, na * q, c.logdetA, c.mstatus, ck.d_ctr, ck.X, st)) return 1;
+        if (factor_batch_multi(h, ck.W, ck.d_ids_nodes, na * q, c.logdetA, c.mstatus, ck.d_ctr, ck.X, st)) return 1;
         if (solve_batch(h, ck.X, ck.d_ids_nodes, na * q, c.vv, c.zv, c.uv, c.gv, ck.vec_elems, st)) return 1;
         post_kernel<<<dim3(q, na), 256, 0, st>>>(c, ck.d_sets, 0, q == 1);
         LAUNCH_CHECK(h);
@@ -480,7 +511,7 @@ static int run_chunk(gprn_handle* h, Chunk& ck, bool init_given, int max_iter, c
         LAUNCH_CHECK(h);
         form_a_kernel<<<dim3(ntri, na * q * p), 256, 0, st>>>(ck.W, ck.K, c.Dv, ck.d_ids_weights, Np);
         LAUNCH_CHECK(h);
-        if (factor_batch(h, ck.W, ck.d_ids_weights, na * q * p, c.logdetA, c.mstatus, ck.d_ctr, ck.X, st)) return 1;
+        if (factor_batch_multi(h, ck.W, ck.d_ids_weights, na * q * p, c.logdetA, c.mstatus, ck.d_ctr, ck.X, st)) return 1;
         if (solve_batch(h, ck.X, ck.d_ids_weights, na * q * p, c.vv, c.zv, c.uv, c.gv, ck.vec_elems, st)) return 1;
         post_kernel<<<dim3(q * p, na), 256, 0, st>>>(c, ck.d_sets, q, q == 1);
         LAUNCH_CHECK(h);
@@ -750,7 +781,7 @@ extern "C" int gprn_predict(gprn_handle* h, const double* hyper, const double* m
     CU(cudaMemsetAsync(ck.d_ctr, 0, sizeof(int) * M, st));
     form_a_kernel<<<dim3(ntri, M), 256, 0, st>>>(ck.W, ck.K, c.Dv, ck.d_ids_all, Np);       // + diag(v), _gp.py:125
     LAUNCH_CHECK(h);
-    if (factor_batch(h, ck.W, ck.d_ids_all, M, c.logdetA, c.mstatus, ck.d_ctr, ck.X, st)) return 1;
+    if (factor_batch_multi(h, ck.W, ck.d_ids_all, M, c.logdetA, c.mstatus, ck.d_ctr, ck.X, st)) return 1;
     if (solve_batch(h, ck.X, ck.d_ids_all, M, c.vv, c.zv, c.uv, c.gv, ck.vec_elems, st)) return 1;   // uv = alpha
     // test points in chunks
     const int TC = 4096;
