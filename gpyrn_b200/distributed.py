@@ -25,6 +25,21 @@ def shard_indices(B, world_size, rank, mode="strided"):
     raise ValueError(f"unknown shard mode {mode!r}")
 
 
+def balanced_assignment(costs, world_size):
+    """Equal-count partition of the sets over ranks that evens out the summed cost (iteration counts of a
+    previous pass are a good predictor: the fixed point a set converges to moves little between passes).
+
+    Sets are sorted by cost and dealt in serpentine order, so every rank receives the same number of sets
+    (+-1) and the per-rank cost sums differ by at most one cost gap per round.  Returns a list of index arrays."""
+    costs = np.asarray(costs, dtype=float)
+    order = np.argsort(-costs, kind="stable")
+    out = [[] for _ in range(world_size)]
+    for pos, i in enumerate(order):
+        rnd, k = divmod(pos, world_size)
+        out[k if rnd % 2 == 0 else world_size - 1 - k].append(int(i))
+    return [np.array(sorted(o), dtype=np.int64) for o in out]
+
+
 def gather_results(local_idx, local_vals, B, group=None, device=None):
     """All-gather per-rank results into full length-B arrays on every rank.
 

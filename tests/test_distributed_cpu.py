@@ -24,6 +24,20 @@ def test_shard_indices_cover_exactly_once():
         D.shard_indices(8, 2, 2)
 
 
+def test_balanced_assignment():
+    rng = np.random.default_rng(0)
+    for B, W in ((16, 8), (17, 4), (8192, 8), (3, 4)):
+        costs = rng.integers(4, 90, B)
+        parts = D.balanced_assignment(costs, W)
+        assert sorted(np.concatenate(parts).tolist()) == list(range(B))
+        sizes = [len(p) for p in parts]
+        assert max(sizes) - min(sizes) <= 1
+        sums = [costs[p].sum() for p in parts]
+        naive = [costs[D.shard_indices(B, W, r)].sum() for r in range(W)]
+        if B >= 2 * W:
+            assert max(sums) - min(sums) <= max(naive) - min(naive) + costs.max()
+
+
 def test_gather_single_process():
     idx = np.array([0, 2, 4])
     out = D.gather_results(idx, {"elbo": np.array([1.0, 2.0, 3.0])}, 5)
