@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "assemble.cuh"
 #include "factor.cuh"
+#include "small.cuh"
 #include "elbo.cuh"
 #include "predict.cuh"
 
@@ -62,13 +63,18 @@ struct gprn_handle {
     std::vector<int32_t> h_tok, h_len, h_par_off, h_npar;
     // workspace (grow only)
     std::vector<DevBuf*> all;
-    DevBuf K, W, X, XK, vecs, state, small, lists, hyper, ysub, ks, pred;
+    DevBuf K, W, X, XK, vecs, state, small, lists, hyper, ysub, ks, pred, scratch;
+    int num_sms = 148;
     // pinned staging
     int* h_lists = nullptr;
     size_t h_lists_n = 0;
     int* h_active = nullptr;
     size_t h_active_n = 0;
 };
+
+static bool use_small_path(const gprn_handle* h) {
+    return h->q == 1 && h->nt <= SMALL_MAX_NT && getenv("GPRN_NO_SMALL") == nullptr;
+}
 
 static int ensure(DevBuf& b, size_t bytes) {
     if (b.bytes >= bytes) return 0;
@@ -106,6 +112,9 @@ static int padded_size(int n) {
 }
 static bool use_two_level(int Np) { return Np >= 512 && Np % OUTER_KB == 0 && getenv("GPRN_NO_TWO_LEVEL") == nullptr; }
 
+// Fused single-kernel pipeline (small.cuh): q == 1 (no cross-node terms, which need the factors in HBM) and N <= 256.
+static bool use_small_path(const gprn_handle* h);
+
 static bool g_attr_done = false;
 static int set_kernel_attrs() {
     if (g_attr_done) return 0;
@@ -116,6 +125,7 @@ static int set_kernel_attrs() {
     CU(cudaFuncSetAttribute(syrk_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM128_SMEM));
     CU(cudaFuncSetAttribute(trtri_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM128_SMEM));
     CU(cudaFuncSetAttribute(trtri_inblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
+    CU(cudaFuncSetAttribute(small_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM));
     CU(cudaFuncSetAttribute(cross_frob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(predict_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     g_attr_done = true;
@@ -141,6 +151,7 @@ extern "C" int gprn_create(int device, int N, int p, int q, const double* time, 
                     std::to_string(prop.major) + std::to_string(prop.minor));
     if (set_kernel_attrs()) return 1;
     gprn_handle* h = new gprn_handle();
+    h->num_sms = prop.multiProcessorCount;
     h->device = device;
     h->N = N;
     h->Np = padded_size(N);
@@ -169,7 +180,7 @@ extern "C" int gprn_create(int device, int N, int p, int q, const double* time, 
     CU(cudaMemcpy(h->d_yerr2, e2.data(), sizeof(double) * p * N, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_ysub_shared, y, sizeof(double) * p * N, cudaMemcpyHostToDevice));
     CU(cudaDeviceSynchronize());   // pageable-memory copies above must have landed before any non-blocking stream runs
-    h->all = {&h->K, &h->W, &h->X, &h->XK, &h->vecs, &h->state, &h->small, &h->lists, &h->hyper, &h->ysub, &h->ks, &h->pred};
+    h->all = {&h->K, &h->W, &h->X, &h->XK, &h->vecs, &h->state, &h->small, &h->lists, &h->hyper, &h->ysub, &h->ks, &h->pred, &h->scratch};
     *out = h;
     return 0;
 }
@@ -359,6 +370,18 @@ static int solve_batch(gprn_handle* h, const double* X, const int* d_ids, int nm
     return 0;
 }
 
+static int small_batch(gprn_handle* h, const double* K, const int* d_ids, int nmat, const double* dvec, const double* vv,
+                       double* uv, double* gv, double* logdet, int* mstatus, int do_inverse, cudaStream_t st) {
+    SmallArgs a;
+    a.K = K; a.ids = d_ids; a.nmat = nmat; a.Np = h->Np; a.dvec = dvec; a.vv = vv;
+    a.scratch = (double*)h->scratch.p; a.uv = uv; a.gv = gv; a.logdet = logdet; a.mstatus = mstatus;
+    a.do_inverse = do_inverse;
+    const int grid = std::min(nmat, 2 * h->num_sms);
+    small_pipeline_kernel<<<grid, 256, SMALL_SMEM, st>>>(a);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
 struct Chunk {
     int nset;
     ElboCtx c;
@@ -369,20 +392,26 @@ struct Chunk {
 
 static size_t per_set_bytes(const gprn_handle* h) {
     const size_t Np = h->Np, M = h->M;
-    size_t mats = (h->q > 1 ? 4 : 3) * M * Np * Np * sizeof(double);
+    size_t mats = (use_small_path(h) ? 1 : (h->q > 1 ? 4 : 3)) * M * Np * Np * sizeof(double);
     size_t vecs = 8 * M * Np * sizeof(double);
     size_t state = 4 * (size_t)h->d * sizeof(double);
     size_t misc = (size_t)h->H * 8 + (size_t)h->p * h->N * 8 + 4096;
     return mats + vecs + state + misc;
 }
 
-static int setup_chunk(gprn_handle* h, int nset, Chunk& ck, bool ysub_per_set) {
+static int setup_chunk(gprn_handle* h, int nset, Chunk& ck, bool ysub_per_set, bool need_factors = false) {
     const size_t Np = h->Np, M = h->M;
     const size_t matbytes = (size_t)nset * M * Np * Np * sizeof(double);
-    if (ensure(h->K, matbytes) || ensure(h->W, matbytes)) return 1;
-    // the inverse factors must hold zeros in their (never written) upper tiles: trtri_outer_kernel reads them
-    if (ensure_zeroed(h->X, matbytes)) return 1;
-    if (h->q > 1 && ensure_zeroed(h->XK, matbytes)) return 1;
+    if (ensure(h->K, matbytes)) return 1;
+    if (use_small_path(h) && !need_factors) {
+        // fused path: factors never reach HBM; a 320 KB scratch per persistent CTA instead
+        if (ensure(h->scratch, (size_t)2 * h->num_sms * SMALL_SCRATCH_DOUBLES * sizeof(double))) return 1;
+    } else {
+        if (ensure(h->W, matbytes)) return 1;
+        // the inverse factors must hold zeros in their (never written) upper tiles: trtri_outer_kernel reads them
+        if (ensure_zeroed(h->X, matbytes)) return 1;
+        if (h->q > 1 && ensure_zeroed(h->XK, matbytes)) return 1;
+    }
     const size_t ve = (size_t)nset * M * Np;
     if (ensure(h->vecs, 7 * ve * sizeof(double))) return 1;
     if (ensure(h->state, 4 * (size_t)nset * h->d * sizeof(double))) return 1;
@@ -468,9 +497,14 @@ static int run_chunk(gprn_handle* h, Chunk& ck, bool init_given, int max_iter, c
     CU(cudaMemsetAsync(c.logdetK, 0, sizeof(double) * (size_t)nset * M, st));
     CU(cudaMemsetAsync(c.mstatus, 0, sizeof(int) * (size_t)nset * M, st));
     CU(cudaMemsetAsync(ck.d_ctr, 0, sizeof(int) * (size_t)nset * M, st));
-    form_a_kernel<<<dim3(ntri, nset * M), 256, 0, st>>>(ck.W, ck.K, nullptr, ck.d_ids_all, Np);
-    LAUNCH_CHECK(h);
-    if (factor_batch_multi(h, ck.W, ck.d_ids_all, nset * M, c.logdetK, c.mstatus, ck.d_ctr, q > 1 ? ck.XK : nullptr, st)) return 1;
+    const bool small = use_small_path(h);
+    if (small) {
+        if (small_batch(h, ck.K, ck.d_ids_all, nset * M, nullptr, nullptr, nullptr, nullptr, c.logdetK, c.mstatus, 0, st)) return 1;
+    } else {
+        form_a_kernel<<<dim3(ntri, nset * M), 256, 0, st>>>(ck.W, ck.K, nullptr, ck.d_ids_all, Np);
+        LAUNCH_CHECK(h);
+        if (factor_batch_multi(h, ck.W, ck.d_ids_all, nset * M, c.logdetK, c.mstatus, ck.d_ctr, q > 1 ? ck.XK : nullptr, st)) return 1;
+    }
     if (q > 1) {
         trmv_upper_norm_kernel<<<dim3(nt, nset * M), 256, 0, st>>>(nullptr, c.gK, ck.XK, nullptr, ck.d_ids_all, Np);
         LAUNCH_CHECK(h);
@@ -494,10 +528,14 @@ static int run_chunk(gprn_handle* h, Chunk& ck, bool init_given, int max_iter, c
         // node phase
         prep_nodes_kernel<<<dim3(q, na), 256, 0, st>>>(c, ck.d_sets);
         LAUNCH_CHECK(h);
-        form_a_kernel<<<dim3(ntri, na * q), 256, 0, st>>>(ck.W, ck.K, c.Dv, ck.d_ids_nodes, Np);
-        LAUNCH_CHECK(h);
-        if (factor_batch_multi(h, ck.W, ck.d_ids_nodes, na * q, c.logdetA, c.mstatus, ck.d_ctr, ck.X, st)) return 1;
-        if (solve_batch(h, ck.X, ck.d_ids_nodes, na * q, c.vv, c.zv, c.uv, c.gv, ck.vec_elems, st)) return 1;
+        if (small) {
+            if (small_batch(h, ck.K, ck.d_ids_nodes, na * q, c.Dv, c.vv, c.uv, c.gv, c.logdetA, c.mstatus, 1, st)) return 1;
+        } else {
+            form_a_kernel<<<dim3(ntri, na * q), 256, 0, st>>>(ck.W, ck.K, c.Dv, ck.d_ids_nodes, Np);
+            LAUNCH_CHECK(h);
+            if (factor_batch_multi(h, ck.W, ck.d_ids_nodes, na * q, c.logdetA, c.mstatus, ck.d_ctr, ck.X, st)) return 1;
+            if (solve_batch(h, ck.X, ck.d_ids_nodes, na * q, c.vv, c.zv, c.uv, c.gv, ck.vec_elems, st)) return 1;
+        }
         post_kernel<<<dim3(q, na), 256, 0, st>>>(c, ck.d_sets, 0, q == 1);
         LAUNCH_CHECK(h);
         if (q > 1) {
@@ -509,10 +547,14 @@ static int run_chunk(gprn_handle* h, Chunk& ck, bool init_given, int max_iter, c
         // weight phase
         prep_weights_kernel<<<dim3(q * p, na), 256, 0, st>>>(c, ck.d_sets);
         LAUNCH_CHECK(h);
-        form_a_kernel<<<dim3(ntri, na * q * p), 256, 0, st>>>(ck.W, ck.K, c.Dv, ck.d_ids_weights, Np);
-        LAUNCH_CHECK(h);
-        if (factor_batch_multi(h, ck.W, ck.d_ids_weights, na * q * p, c.logdetA, c.mstatus, ck.d_ctr, ck.X, st)) return 1;
-        if (solve_batch(h, ck.X, ck.d_ids_weights, na * q * p, c.vv, c.zv, c.uv, c.gv, ck.vec_elems, st)) return 1;
+        if (small) {
+            if (small_batch(h, ck.K, ck.d_ids_weights, na * q * p, c.Dv, c.vv, c.uv, c.gv, c.logdetA, c.mstatus, 1, st)) return 1;
+        } else {
+            form_a_kernel<<<dim3(ntri, na * q * p), 256, 0, st>>>(ck.W, ck.K, c.Dv, ck.d_ids_weights, Np);
+            LAUNCH_CHECK(h);
+            if (factor_batch_multi(h, ck.W, ck.d_ids_weights, na * q * p, c.logdetA, c.mstatus, ck.d_ctr, ck.X, st)) return 1;
+            if (solve_batch(h, ck.X, ck.d_ids_weights, na * q * p, c.vv, c.zv, c.uv, c.gv, ck.vec_elems, st)) return 1;
+        }
         post_kernel<<<dim3(q * p, na), 256, 0, st>>>(c, ck.d_sets, q, q == 1);
         LAUNCH_CHECK(h);
         if (q > 1) {   // quadratic forms with the reference's vector pairing (quirk Q4)
@@ -758,7 +800,7 @@ extern "C" int gprn_predict(gprn_handle* h, const double* hyper, const double* m
     const int N = h->N, Np = h->Np, nt = h->nt, M = h->M, q = h->q, p = h->p;
     const int ntri = nt * (nt + 1) / 2;
     Chunk ck;
-    if (setup_chunk(h, 1, ck, false)) return 1;
+    if (setup_chunk(h, 1, ck, false, true)) return 1;
     ElboCtx& c = ck.c;
     CU(cudaMemcpyAsync((void*)c.hyper, hyper, sizeof(double) * h->H, cudaMemcpyHostToDevice, st));
     // variational means -> vv, variances -> Dv (zero padded, one vector per GP in matrix order)

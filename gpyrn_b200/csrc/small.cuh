@@ -1,0 +1,244 @@
+// small.cuh -- fused per-matrix pipeline for small matrices (Np <= 256, i.e. at most 4x4 tiles of 64).
+//
+// One persistent CTA takes a matrix through the WHOLE per-iteration chain
+//     A = K + diag(D)  ->  L = chol(A)  ->  X = L^-1  ->  g = colnorm2(X),  u = X^T (X v),  logdet(A)
+// and only the vectors g, u and the scalar log-det leave the chip.  K is read from HBM exactly once
+// (lower tiles); L / X live in a 10-tile (320 KB) per-CTA scratch that stays L2 resident
+// (296 CTAs x 320 KB = 95 MB < 126 MB L2) -- X tiles overwrite the L tiles they no longer need.
+// The building blocks are the same as in factor.cuh: DMMA m8n8k4 tile products (mma_tile), the
+// register-resident 64x64 Cholesky (potrf64) and thread-per-vector substitution (subst_lower).
+// Replaces, for q == 1 and N <= 256, form_a + panel_col + trtri_* + trmv_* (one launch instead of ~10 and
+// none of their HBM round trips).  256 threads: warps 0-3 and 4-7 work on two tiles at a time.
+#pragma once
+#include "common.cuh"
+
+namespace gprn {
+
+#define SMALL_MAX_NT 4
+#define SMALL_TILES 10
+#define SMALL_LDV 129
+#define SMALL_SCRATCH_DOUBLES (SMALL_TILES * NB * NB)
+// 3 operand tiles + col(128) + pivs(64) + rd(64) + gacc(256) + zacc(256) + vloc(256)
+#define SMALL_SMEM ((3 * NB * LDT + 4 * NB + 3 * SMALL_MAX_NT * NB) * sizeof(double))
+
+struct SmallArgs {
+    const double* K;       // [.][Np][Np] assembled covariance matrices (lower tiles)
+    const int* ids;        // matrix ids
+    int nmat, Np;
+    const double* dvec;    // [id][Np] diagonal to add, or null
+    const double* vv;      // [id][Np] right-hand side v (needed when do_inverse)
+    double* scratch;       // gridDim.x * SMALL_SCRATCH_DOUBLES
+    double* uv;            // out [id][Np]  u = X^T X v
+    double* gv;            // out [id][Np]  g = colnorm2(X) = diag(A^-1)
+    double* logdet;        // out [id]
+    int* mstatus;          // out [id], set to 1 on a non-positive pivot
+    int do_inverse;
+};
+
+__device__ __forceinline__ double* small_tile(double* scratch, int I, int J) {
+    return scratch + (size_t)(I * (I + 1) / 2 + J) * (NB * NB);
+}
+
+__global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
+    extern __shared__ double smem[];
+    double* Bs = smem;                 // B operand / potrf input+output (L_kk) / A operand in the inverse
+    double* As0 = smem + NB * LDT;
+    double* As1 = smem + 2 * NB * LDT;
+    double* V = As0;                   // substitution vectors (stride 129), aliases As0/As1
+    double* col = smem + 3 * NB * LDT;
+    double* pivs = col + 2 * NB;
+    double* rd = pivs + NB;
+    double* gacc = rd + NB;            // [Np]
+    double* zacc = gacc + SMALL_MAX_NT * NB;
+    double* vloc = zacc + SMALL_MAX_NT * NB;
+    __shared__ int bad;
+    const int Np = a.Np, nt = Np / NB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = warp >> 2, w4 = warp & 3, wm = w4 >> 1, wn = w4 & 1, tid4 = tid & 127;
+    const int r = lane >> 2, c = lane & 3;
+    double* sc = a.scratch + (size_t)blockIdx.x * SMALL_SCRATCH_DOUBLES;
+
+    for (int mi = blockIdx.x; mi < a.nmat; mi += gridDim.x) {
+        const int id = a.ids[mi];
+        const double* Km = a.K + (size_t)id * Np * Np;
+        const double* dv = a.dvec ? a.dvec + (size_t)id * Np : nullptr;
+        double logsum = 0.0;
+        if (tid == 0) bad = 0;
+        __syncthreads();
+
+        // ================= Cholesky, left-looking over tile columns =================
+        // Column k is done in two sub-rounds of two tiles: s = 0 -> (k, k+1), s = 1 -> (k+2, k+3); warps 0-3 take
+        // the first tile of a sub-round, warps 4-7 the second.  One accumulator set is live at a time.
+        for (int k = 0; k < nt; k++) {
+            for (int s = 0; s < 2 && k + 2 * s < nt; s++) {
+                const int it = k + 2 * s + grp;
+                const bool have = it < nt;
+                double acc[4][4][2];
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+#pragma unroll
+                    for (int y = 0; y < 4; y++) {
+                        const int m = wm * 32 + x * 8 + r, n = wn * 32 + y * 8 + 2 * c;
+                        double2 v = make_double2(0.0, 0.0);
+                        if (have) {
+                            v = *reinterpret_cast<const double2*>(Km + (size_t)(it * NB + m) * Np + k * NB + n);
+                            if (dv && it == k) {
+                                if (m == n) v.x += dv[k * NB + m];
+                                if (m == n + 1) v.y += dv[k * NB + m];
+                            }
+                        }
+                        acc[x][y][0] = v.x;
+                        acc[x][y][1] = v.y;
+                    }
+                const bool diag = (s == 0 && grp == 0);
+                for (int kp = 0; kp < k; kp++) {
+                    load_tile<false>(Bs, small_tile(sc, k, kp), NB, tid, 256);
+                    if (have && !diag) load_tile<false>(grp ? As1 : As0, small_tile(sc, it, kp), NB, tid4, 128);
+                    __syncthreads();
+                    if (have) mma_tile<true>(acc, diag ? Bs : (grp ? As1 : As0), Bs, wm, wn, lane);
+                    __syncthreads();
+                }
+                if (s == 0) {
+#pragma unroll
+                    for (int x = 0; x < 4; x++)
+#pragma unroll
+                        for (int y = 0; y < 4; y++) {
+                            const int m = wm * 32 + x * 8 + r, n = wn * 32 + y * 8 + 2 * c;
+                            if (grp == 0) {
+                                Bs[m * LDV + n] = acc[x][y][0];
+                                Bs[m * LDV + n + 1] = acc[x][y][1];
+                            } else if (have) {
+                                V[n * SMALL_LDV + NB + m] = acc[x][y][0];
+                                V[(n + 1) * SMALL_LDV + NB + m] = acc[x][y][1];
+                            }
+                        }
+                    __syncthreads();
+                    potrf64(Bs, LDV, Bs, rd, col, pivs, &bad);
+                    if (tid >= NB && tid < 2 * NB && k + 1 < nt) subst_lower(Bs, LDT, rd, V, SMALL_LDV, tid);
+                    if (tid < 32) logsum += log(pivs[tid]) + log(pivs[tid + 32]);
+                    __syncthreads();
+                    double* dkk = small_tile(sc, k, k);
+                    for (int e = tid; e < NB * NB; e += 256) dkk[e] = Bs[(e >> 6) * LDT + (e & 63)];
+                    if (k + 1 < nt) {
+                        double* d1 = small_tile(sc, k + 1, k);
+                        for (int e = tid; e < NB * NB; e += 256) d1[e] = V[(e & 63) * SMALL_LDV + NB + (e >> 6)];
+                    }
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 4; x++)
+#pragma unroll
+                        for (int y = 0; y < 4; y++) {
+                            const int m = wm * 32 + x * 8 + r, n = wn * 32 + y * 8 + 2 * c;
+                            if (have) {
+                                V[n * SMALL_LDV + grp * NB + m] = acc[x][y][0];
+                                V[(n + 1) * SMALL_LDV + grp * NB + m] = acc[x][y][1];
+                            }
+                        }
+                    load_tile<false>(Bs, small_tile(sc, k, k), NB, tid, 256);     // L_kk back from the scratch
+                    __syncthreads();
+                    if (tid < NB) rd[tid] = 1.0 / Bs[tid * LDT + tid];
+                    __syncthreads();
+                    if (tid < 2 * NB && k + 2 + (tid >> 6) < nt) subst_lower(Bs, LDT, rd, V, SMALL_LDV, tid);
+                    __syncthreads();
+                    if (have) {
+                        double* d2 = small_tile(sc, it, k);
+                        for (int e = tid4; e < NB * NB; e += 128) d2[e] = V[(e & 63) * SMALL_LDV + grp * NB + (e >> 6)];
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (tid < 32) {
+            logsum = warp_sum(logsum);
+            if (tid == 0) {
+                a.logdet[id] = logsum;
+                if (bad) a.mstatus[id] = 1;
+            }
+        }
+        if (!a.do_inverse) continue;
+
+        // ================= inverse by block rows; X tiles overwrite the L tiles =================
+        for (int e = tid; e < Np; e += 256) {
+            gacc[e] = 0.0;
+            zacc[e] = 0.0;
+            vloc[e] = a.vv[(size_t)id * Np + e];
+        }
+        __syncthreads();
+        for (int i = 0; i < nt; i++) {
+            for (int j0 = 0; j0 <= i; j0 += 2) {
+                const int j = j0 + grp;                 // this group's right-hand-side tile (j == i: identity)
+                double acc[4][4][2];
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+#pragma unroll
+                    for (int y = 0; y < 4; y++) acc[x][y][0] = acc[x][y][1] = 0.0;
+                for (int k = j0; k < i; k++) {
+                    load_tile<false>(Bs, small_tile(sc, i, k), NB, tid, 256);                       // L_ik (shared A operand)
+                    const bool part = (j < i) && (k >= j);
+                    if (part) load_tile<true>(grp ? As1 : As0, small_tile(sc, k, j), NB, tid4, 128);   // X_kj^T
+                    __syncthreads();
+                    if (part) mma_tile<true>(acc, Bs, grp ? As1 : As0, wm, wn, lane);
+                    __syncthreads();
+                }
+                // stage right-hand sides: vector = column n of the tile, element m at V[m*ldv + grp*64 + n]
+                if (j < i) {
+#pragma unroll
+                    for (int x = 0; x < 4; x++)
+#pragma unroll
+                        for (int y = 0; y < 4; y++) {
+                            const int m = wm * 32 + x * 8 + r, n = wn * 32 + y * 8 + 2 * c;
+                            V[m * SMALL_LDV + grp * NB + n] = acc[x][y][0];
+                            V[m * SMALL_LDV + grp * NB + n + 1] = acc[x][y][1];
+                        }
+                } else if (j == i) {
+                    for (int e = tid4; e < NB * NB; e += 128) V[(e >> 6) * SMALL_LDV + grp * NB + (e & 63)] = ((e >> 6) == (e & 63)) ? 1.0 : 0.0;
+                }
+                load_tile<false>(Bs, small_tile(sc, i, i), NB, tid, 256);                           // L_ii
+                __syncthreads();
+                if (tid < NB) rd[tid] = 1.0 / Bs[tid * LDT + tid];
+                __syncthreads();
+                const int jt = j0 + (tid >> 6);          // tile handled by thread tid < 128 in the substitution
+                if (tid < 2 * NB && jt <= i) subst_lower(Bs, LDT, rd, V, SMALL_LDV, tid, jt == i ? ((tid & 63) >> 3) : 0);
+                __syncthreads();
+                if (tid < 2 * NB && jt <= i) {
+                    // column sums of squares of X_ij (thread = column) -> g_j ; single writer per (j, n) and round
+                    double sg = 0.0;
+                    for (int m = 0; m < NB; m++) { double x = V[m * SMALL_LDV + tid]; sg = fma(x, x, sg); }
+                    gacc[jt * NB + (tid & 63)] += sg;
+                }
+                if (tid >= 2 * NB && tid < 3 * NB) {
+                    // row sums X_ij v_j (thread = row) -> z_i ; one thread adds both tiles of the round (fixed order)
+                    const int m = tid - 2 * NB;
+                    double sz = 0.0;
+                    for (int g2 = 0; g2 < 2; g2++) {
+                        const int jj = j0 + g2;
+                        if (jj <= i)
+                            for (int n = 0; n < NB; n++) sz = fma(V[m * SMALL_LDV + g2 * NB + n], vloc[jj * NB + n], sz);
+                    }
+                    zacc[i * NB + m] += sz;
+                }
+                if (j <= i) {
+                    double* dx = small_tile(sc, i, j);
+                    for (int e = tid4; e < NB * NB; e += 128) dx[e] = V[(e >> 6) * SMALL_LDV + grp * NB + (e & 63)];
+                }
+                __syncthreads();
+            }
+        }
+        // u_j[n] = sum_{i >= j} sum_m X_ij[m][n] z_i[m]   (X tiles from the L2-resident scratch)
+        {
+            const int j = tid >> 6, n = tid & 63;
+            if (j < nt) {
+                double su = 0.0;
+                for (int i = j; i < nt; i++) {
+                    const double* xt = small_tile(sc, i, j);
+                    for (int m = 0; m < NB; m++) su = fma(xt[m * NB + n], zacc[i * NB + m], su);
+                }
+                a.uv[(size_t)id * Np + tid] = su;
+                a.gv[(size_t)id * Np + tid] = gacc[tid];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace gprn
