@@ -260,9 +260,9 @@ __global__ void __launch_bounds__(128) trtri_row_kernel(double* __restrict__ X, 
 
 // Trailing update after the 256-column panel starting at column c0: for 128x128 tiles (TI >= TJ) of the
 // trailing square starting at t0 = c0 + 256:  C -= L[rows, c0:c0+256] L[cols, c0:c0+256]^T.
-// grid = (n(n+1)/2 with n = (Np - t0)/128, nmat), block = 256, dynamic smem GEMM128_SMEM.
-__global__ void __launch_bounds__(256) syrk_outer_kernel(double* __restrict__ W, const int* __restrict__ ids, int Np,
-                                                         int c0) {
+// grid = (n(n+1)/2 with n = (Np - t0)/128, nmat), block = G_THREADS, dynamic smem GEMM128_SMEM.
+__global__ void __launch_bounds__(G_THREADS) syrk_outer_kernel(double* __restrict__ W, const int* __restrict__ ids,
+                                                               int Np, int c0) {
     extern __shared__ double smem[];
     int TI, TJ;
     tri_decode(blockIdx.x, TI, TJ);
@@ -270,20 +270,23 @@ __global__ void __launch_bounds__(256) syrk_outer_kernel(double* __restrict__ W,
     const int r0 = t0 + TI * G_BM, n0 = t0 + TJ * G_BN;
     const int id = ids[blockIdx.y];
     double* Wm = W + (size_t)id * Np * Np;
-    double acc[8][4][2];
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    gemm128_mainloop<false>(acc, smem, Wm + (size_t)r0 * Np + c0, Np, Wm + (size_t)n0 * Np + c0, Np, OUTER_KB);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3;
     const int r = lane >> 2, c = lane & 3;
     double* C = Wm + (size_t)r0 * Np + n0;
+    // The products are summed on their own and subtracted from C once at the end: starting the accumulators at
+    // -C (which would make the epilogue a pure store) rounds every partial sum at the magnitude of C and costs
+    // measurable ELBO parity at N >= 2048 (c5 anchor: 1e-10 bar missed), for no gain in time.
+    double acc[G_MI][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < G_MI; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    gemm128_mainloop<false>(acc, smem, Wm + (size_t)r0 * Np + c0, Np, Wm + (size_t)n0 * Np + c0, Np, OUTER_KB);
+#pragma unroll
+    for (int i = 0; i < G_MI; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            double2* p = reinterpret_cast<double2*>(C + (size_t)(wm * 64 + i * 8 + r) * Np + wn * 32 + j * 8 + 2 * c);
+            double2* p = reinterpret_cast<double2*>(C + (size_t)(wm * G_WM + i * 8 + r) * Np + wn * 32 + j * 8 + 2 * c);
             double2 v = *p;
             v.x -= acc[i][j][0];
             v.y -= acc[i][j][1];
@@ -293,8 +296,8 @@ __global__ void __launch_bounds__(256) syrk_outer_kernel(double* __restrict__ W,
 
 // Inverse, block row of 256 rows starting at R0: X[rows, 0:R0] = - L[rows, n0:R0] X[n0:R0, cols] (the part of
 // the row-sweep sum that lies above the block), 128x128 tiles.  X must hold zeros in its upper tiles.
-// grid = (2 * R0/128, nmat), block = 256, dynamic smem GEMM128_SMEM.
-__global__ void __launch_bounds__(256) trtri_outer_kernel(double* __restrict__ X, const double* __restrict__ W,
+// grid = (2 * R0/128, nmat), block = G_THREADS, dynamic smem GEMM128_SMEM.
+__global__ void __launch_bounds__(G_THREADS) trtri_outer_kernel(double* __restrict__ X, const double* __restrict__ W,
                                                           const int* __restrict__ ids, int Np, int R0) {
     extern __shared__ double smem[];
     const int ncol = R0 / G_BN;
@@ -303,9 +306,9 @@ __global__ void __launch_bounds__(256) trtri_outer_kernel(double* __restrict__ X
     const int id = ids[blockIdx.y];
     const double* Wm = W + (size_t)id * Np * Np;
     double* Xm = X + (size_t)id * Np * Np;
-    double acc[8][4][2];
+    double acc[G_MI][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < G_MI; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
     gemm128_mainloop<true>(acc, smem, Wm + (size_t)r0 * Np + n0, Np, Xm + (size_t)n0 * Np + n0, Np, R0 - n0);
@@ -313,11 +316,11 @@ __global__ void __launch_bounds__(256) trtri_outer_kernel(double* __restrict__ X
     const int r = lane >> 2, c = lane & 3;
     double* C = Xm + (size_t)r0 * Np + n0;
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < G_MI; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             double2 v = make_double2(-acc[i][j][0], -acc[i][j][1]);
-            *reinterpret_cast<double2*>(C + (size_t)(wm * 64 + i * 8 + r) * Np + wn * 32 + j * 8 + 2 * c) = v;
+            *reinterpret_cast<double2*>(C + (size_t)(wm * G_WM + i * 8 + r) * Np + wn * 32 + j * 8 + 2 * c) = v;
         }
 }
 

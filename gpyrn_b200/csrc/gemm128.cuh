@@ -4,9 +4,9 @@
 //   A : row-major, k contiguous ("[m][k]").
 //   B : !B_KMAJOR  row-major [n][k], k contiguous   (NT product, e.g. L_ik L_jk^T)
 //        B_KMAJOR  row-major [k][n], n contiguous   (NN product, e.g. L_ik X_kj)
-// 256 threads = 8 warps laid out 2 (M) x 4 (N); each warp owns 64x32 = 8x4 DMMA accumulator tiles
-// (64 doubles per thread).  Per k-step of 4 a warp issues 12 shared-memory fragment loads for 32
-// DMMAs.  Shared-memory strides (20 / 132 doubles = 32 B mod 128 B) make the fragment loads of a
+// G_THREADS = 512: 16 warps laid out 4 (M) x 4 (N), each owning 32x32 = 4x4 DMMA accumulator tiles (32 doubles
+// per thread; 4 warps per scheduler hide the DMMA / shared-memory latencies better than the 8-warp, 64x32
+// variant, which measured 71 % DMMA-pipe utilisation).  Per k-step of 4 a warp issues 8 fragment loads for 16 DMMAs.  Shared-memory strides (20 / 132 doubles = 32 B mod 128 B) make the fragment loads of a
 // half-warp hit 16 distinct 8-byte slots.
 #pragma once
 #include "common.cuh"
@@ -16,6 +16,13 @@ namespace gprn {
 #define G_BM 128
 #define G_BN 128
 #define G_BK 16
+#ifndef G_THREADS
+#define G_THREADS 512             // 16 warps, 4 (M) x 4 (N), 32x32 accumulator tile per warp
+#endif
+#define G_WARPS_N 4
+#define G_WARPS_M (G_THREADS / 32 / G_WARPS_N)
+#define G_WM (G_BM / G_WARPS_M)     // rows per warp: 32 (512 threads) or 64 (256 threads)
+#define G_MI (G_WM / 8)             // m8 tiles per warp
 #ifndef G_STAGES
 #define G_STAGES 4
 #endif
@@ -41,29 +48,30 @@ __device__ __forceinline__ void gemm128_load_stage(double* As, double* Bs, const
                                                    const double* __restrict__ B, size_t ldb, int k0, int tid) {
     // A: 128 rows x 8 chunks of 2 doubles
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-        int ch = tid + 256 * u, row = ch >> 3, kc = ch & 7;
+    for (int u = 0; u < 1024 / G_THREADS; u++) {
+        int ch = tid + G_THREADS * u, row = ch >> 3, kc = ch & 7;
         cp_async16(As + row * G_LDA + 2 * kc, A + (size_t)row * lda + k0 + 2 * kc);
     }
     if (!B_KMAJOR) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            int ch = tid + 256 * u, row = ch >> 3, kc = ch & 7;
+        for (int u = 0; u < 1024 / G_THREADS; u++) {
+            int ch = tid + G_THREADS * u, row = ch >> 3, kc = ch & 7;
             cp_async16(Bs + row * G_LDB_NT + 2 * kc, B + (size_t)row * ldb + k0 + 2 * kc);
         }
     } else {
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            int ch = tid + 256 * u, k = ch >> 6, nc = ch & 63;
+        for (int u = 0; u < 1024 / G_THREADS; u++) {
+            int ch = tid + G_THREADS * u, k = ch >> 6, nc = ch & 63;
             cp_async16(Bs + k * G_LDB_NN + 2 * nc, B + (size_t)(k0 + k) * ldb + 2 * nc);
         }
     }
 }
 
 // acc += A(128 x K) * B over k in [0, K), K a multiple of 16.  A / B point at the k = 0 corner of
-// the CTA's row / column panel.  smem: GEMM128_SMEM bytes.  All 256 threads call.
+// the CTA's row / column panel.  smem: GEMM128_SMEM bytes.  All G_THREADS threads call.
+// Accumulator (i, j, e) of a thread is element (wm*G_WM + i*8 + lane/4, wn*32 + j*8 + 2*(lane%4) + e) of the tile.
 template <bool B_KMAJOR>
-__device__ __forceinline__ void gemm128_mainloop(double (&acc)[8][4][2], double* smem, const double* __restrict__ A,
+__device__ __forceinline__ void gemm128_mainloop(double (&acc)[G_MI][4][2], double* smem, const double* __restrict__ A,
                                                  size_t lda, const double* __restrict__ B, size_t ldb, int K) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wm = warp >> 2, wn = warp & 3;
@@ -89,18 +97,18 @@ __device__ __forceinline__ void gemm128_mainloop(double (&acc)[8][4][2], double*
             cp_async_commit();
         }
         const int st = kt % G_STAGES;
-        const double* as = As0 + st * G_A_STAGE + (wm * 64 + r) * G_LDA + c;
+        const double* as = As0 + st * G_A_STAGE + (wm * G_WM + r) * G_LDA + c;
         const double* bs = B_KMAJOR ? Bs0 + st * BST + c * G_LDB_NN + wn * 32 + r
                                     : Bs0 + st * BST + (wn * 32 + r) * G_LDB_NT + c;
 #pragma unroll
         for (int kk = 0; kk < G_BK; kk += 4) {
-            double a[8], b[4];
+            double a[G_MI], b[4];
 #pragma unroll
-            for (int i = 0; i < 8; i++) a[i] = as[i * 8 * G_LDA + kk];
+            for (int i = 0; i < G_MI; i++) a[i] = as[i * 8 * G_LDA + kk];
 #pragma unroll
             for (int j = 0; j < 4; j++) b[j] = B_KMAJOR ? bs[kk * G_LDB_NN + j * 8] : bs[j * 8 * G_LDB_NT + kk];
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < G_MI; i++)
 #pragma unroll
                 for (int j = 0; j < 4; j++) dmma884(acc[i][j], a[i], b[j]);
         }

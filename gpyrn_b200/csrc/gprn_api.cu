@@ -303,7 +303,7 @@ static int factor_batch(gprn_handle* h, double* W, const int* d_ids, int nmat, d
         if (ke < nt) {
             if (two) {
                 const int n128 = (Np - ke * NB) / G_BM;
-                syrk_outer_kernel<<<dim3(n128 * (n128 + 1) / 2, nmat), 256, GEMM128_SMEM, st>>>(W, d_ids, Np, k0 * NB);
+                syrk_outer_kernel<<<dim3(n128 * (n128 + 1) / 2, nmat), G_THREADS, GEMM128_SMEM, st>>>(W, d_ids, Np, k0 * NB);
             } else {
                 const int n = nt - ke;
                 syrk_update_kernel<<<dim3(n * (n + 1) / 2, nmat), 128, 2 * TILE_SMEM, st>>>(W, d_ids, Np, k0, ke);
@@ -317,7 +317,7 @@ static int factor_batch(gprn_handle* h, double* W, const int* d_ids, int nmat, d
         if (two || nt <= 4) {
             for (int i0 = 0; i0 < nt; i0 += 4) {
                 if (i0 > 0) {
-                    trtri_outer_kernel<<<dim3(2 * (i0 * NB / G_BN), nmat), 256, GEMM128_SMEM, st>>>(X, W, d_ids, Np, i0 * NB);
+                    trtri_outer_kernel<<<dim3(2 * (i0 * NB / G_BN), nmat), G_THREADS, GEMM128_SMEM, st>>>(X, W, d_ids, Np, i0 * NB);
                     LAUNCH_CHECK(h);
                 }
                 const int ncol = std::min(i0 + 4, nt) - 1;
