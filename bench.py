@@ -35,7 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    "c4": dict(N=4096, p=4, q=2, node="M52", sets_per_gpu=2, seed=102,
+    "c4": dict(N=4096, p=4, q=2, node="M52", sets_per_gpu=4, seed=102,
                name="C4 synth(N=4096,p=4,q=2,Matern52 nodes, SE weights), batched ELBOcalc to convergence"),
     "c3": dict(N=256, p=4, q=1, node="QP", sets_per_gpu=8192, seed=101,
                name="C3 synth(N=256,p=4,q=1,QuasiPeriodic node, SE weights), 8192 hyper sets per GPU"),

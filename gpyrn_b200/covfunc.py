@@ -3,13 +3,15 @@
 Same public surface as the reference's ``gpyrn.covfunc`` for the kernels on the hot path
 (``SquaredExponential``, ``Periodic``, ``QuasiPeriodic``, ``RationalQuadratic``, ``Matern32``,
 ``Matern52``, ``WhiteNoise`` and their ``+`` / ``*`` compositions; reference gpyrn/covfunc.py:5-80,
-128-288, 355-396): ``.pars`` float64 array, ``_param_names``, ``_tag``, ``get_parameters`` /
+128-288, 355-396), plus the four cheap "next" kernels of SURVEY.md 8(f).3 (``Constant``, ``RQP``, ``Cosine``,
+``Exponential``; covfunc.py:107-125, 291-352): ``.pars`` float64 array, ``_param_names``, ``_tag``, ``get_parameters`` /
 ``set_parameters``, ``k(r)`` on an array of lags.
 
 The objects hold parameters and structure only.  All arithmetic happens on the GPU: ``k(r)`` ships
 ``r`` through the C ABI (``gprn_keval``), and the inference engine serialises the kernel into a
 postfix program (``program()``) that the assembly kernels interpret.  The other kernels of the
-reference (Constant, RQP, Cosine, Exponential, Linear, ... -- SURVEY.md section 2 row 2) are outside
+reference (Linear, GammaExp, Polynomial, Piecewise, Paciorek, the *Periodic variants ... -- SURVEY.md section 2
+row 2) are outside
 the hot-path scope of this package.
 """
 import numpy as np
@@ -18,6 +20,7 @@ from . import _lib
 
 # opcodes of include/gprn_b200.h
 OP_SE, OP_PER, OP_QP, OP_RQ, OP_M32, OP_M52, OP_WN, OP_ADD, OP_MUL = 1, 2, 3, 4, 5, 6, 7, 100, 101
+OP_CONST, OP_RQP, OP_COS, OP_EXP = 8, 9, 10, 11
 
 
 class covFunction:
@@ -115,6 +118,47 @@ class Sum(_operator):
 class Multiplication(_operator):
     """k1(r) * k2(r)"""
     _symbol, _join = '*', OP_MUL
+
+
+class Constant(covFunction):
+    r""":math:`K_{ij} = c^2`"""
+    _param_names = 'c',
+    _tag = 'C'
+    _opcode = OP_CONST
+
+    def __init__(self, c: float):
+        super().__init__(c)
+
+
+class RQP(covFunction):
+    r"""Periodic times rational quadratic:
+    :math:`\theta^2 \exp[-2\sin^2(\pi r/P)/\ell_p^2]\,[1 + r^2/(2\alpha\ell_e^2)]^{-\alpha}`"""
+    _param_names = 'theta', 'alpha', 'elle', 'ellp', 'P'
+    _tag = 'RQP'
+    _opcode = OP_RQP
+
+    def __init__(self, theta: float, alpha: float, elle: float, P: float, ellp: float):
+        super().__init__(theta, alpha, elle, P, ellp)
+
+
+class Cosine(covFunction):
+    r""":math:`\theta^2 \cos(2\pi |r| / P)`"""
+    _param_names = 'theta', 'P'
+    _tag = 'COS'
+    _opcode = OP_COS
+
+    def __init__(self, theta: float, P: float):
+        super().__init__(theta, P)
+
+
+class Exponential(covFunction):
+    r""":math:`\theta^2 \exp(-|r|/\ell)`"""
+    _param_names = 'theta', 'ell'
+    _tag = 'EXP'
+    _opcode = OP_EXP
+
+    def __init__(self, theta: float, ell: float):
+        super().__init__(theta, ell)
 
 
 class WhiteNoise(covFunction):

@@ -69,6 +69,28 @@ __device__ __forceinline__ double eval_prog(const int32_t* __restrict__ tok, int
                 st[sp++] = (on_diag_pos || wn_const) ? w * w : 0.0;
                 pp += 1;
             } break;
+            case GPRN_OP_CONST: {  // covfunc.py:122-125
+                double cst = par[pp];
+                st[sp++] = cst * cst;
+                pp += 1;
+            } break;
+            case GPRN_OP_RQP: {  // covfunc.py:307-310
+                double th = par[pp], al = par[pp + 1], le = par[pp + 2], P = par[pp + 3], lp = par[pp + 4];
+                double s = sin((M_PI * ar) / P);
+                st[sp++] = ((th * th) * exp(((-2.0) * (s * s)) / (lp * lp))) *
+                           pow(1.0 + (r * r) / ((2.0 * al) * (le * le)), -al);
+                pp += 5;
+            } break;
+            case GPRN_OP_COS: {  // covfunc.py:327-328
+                double th = par[pp], P = par[pp + 1];
+                st[sp++] = (th * th) * cos(((2.0 * M_PI) * ar) / P);
+                pp += 2;
+            } break;
+            case GPRN_OP_EXP: {  // covfunc.py:351-352
+                double th = par[pp], l = par[pp + 1];
+                st[sp++] = (th * th) * exp((-ar) / l);
+                pp += 2;
+            } break;
             case GPRN_OP_ADD: {
                 sp--;
                 st[sp - 1] = st[sp - 1] + st[sp];

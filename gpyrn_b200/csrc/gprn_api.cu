@@ -219,6 +219,10 @@ static int op_npar(int op) {
         case GPRN_OP_M32: return 2;
         case GPRN_OP_M52: return 2;
         case GPRN_OP_WN: return 1;
+        case GPRN_OP_CONST: return 1;
+        case GPRN_OP_RQP: return 5;
+        case GPRN_OP_COS: return 2;
+        case GPRN_OP_EXP: return 2;
         case GPRN_OP_ADD: case GPRN_OP_MUL: return 0;
         default: return -1;
     }

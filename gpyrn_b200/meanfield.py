@@ -386,17 +386,20 @@ class inference:
         elbo, mu_out, var_out, _, _ = self._run_elbo(nodes, weights, means, jitters, 1, mu, var)
         return elbo, mu_out, var_out, None, None
 
-    def ELBO_batch(self, parameters, max_iter=None, return_info=False):
+    def ELBO_batch(self, parameters, max_iter=None, return_info=False, mu=None, var=None, return_state=False):
         """
-        ELBO of B hyper-parameter sets in one device call (every set starts from 'init').
+        ELBO of B hyper-parameter sets in one device call.
 
         Args:
             parameters: array (B, n_parameters) or (B, number of free parameters), ``get_parameters`` order
             max_iter: per-evaluation iteration cap (default 10000)
             return_info: also return (iterations, status) arrays
+            mu, var: optional per-set initial variational state, arrays (B, d) -- the batched form of
+                ``ELBOcalc(mu='previous')`` for chains / walkers that carry their own state; default 'init'
+            return_state: also return the final (mu, var), arrays (B, d), to be fed back on the next call
 
         Returns:
-            elbo: array (B,)
+            elbo (B,) [, iterations (B,), status (B,)] [, mu (B, d), var (B, d)]
         """
         self._require_components()
         P = np.atleast_2d(np.asarray(parameters, dtype=float))
@@ -428,10 +431,23 @@ class inference:
         elbo = np.empty(B)
         iters = np.zeros(B, dtype=np.int32)
         status = np.zeros(B, dtype=np.int32)
-        _lib.check(_lib.lib().gprn_elbo_batched(self._h(), B, _lib.dptr(hyper), _lib.dptr(ysub), shared, 0, None,
-                                                None, -1 if max_iter is None else max_iter, _lib.dptr(elbo),
+        init_mode, mu_io, var_io = 0, None, None
+        if mu is not None or var is not None:
+            if mu is None or var is None:
+                raise ValueError('provide both mu and var, or neither')
+            mu_io = _lib.f64(np.array(mu, dtype=float).reshape(B, self.d))
+            var_io = _lib.f64(np.array(var, dtype=float).reshape(B, self.d))
+            init_mode = 1
+        elif return_state:
+            mu_io, var_io = np.empty((B, self.d)), np.empty((B, self.d))
+        _lib.check(_lib.lib().gprn_elbo_batched(self._h(), B, _lib.dptr(hyper), _lib.dptr(ysub), shared, init_mode,
+                                                _lib.dptr(mu_io), _lib.dptr(var_io),
+                                                -1 if max_iter is None else max_iter, _lib.dptr(elbo),
                                                 _lib.iptr(iters), _lib.iptr(status), None))
-        return (elbo, iters, status) if return_info else elbo
+        out = (elbo, iters, status) if return_info else (elbo,)
+        if return_state:
+            out = out + (mu_io, var_io)
+        return out if len(out) > 1 else out[0]
 
     def _assign_means(self, values):
         rest = np.asarray(values, dtype=float)

@@ -37,6 +37,11 @@ enum {
     GPRN_OP_M32 = 5, /* theta, ell            */
     GPRN_OP_M52 = 6, /* theta, ell            */
     GPRN_OP_WN = 7,  /* w                     */
+    /* SURVEY 8(f).3 "next" kernels: covfunc.py:107-125 (Constant), :291-310 (RQP), :313-328 (Cosine), :331-352 (Exponential) */
+    GPRN_OP_CONST = 8, /* c                              */
+    GPRN_OP_RQP = 9,   /* theta, alpha, elle, P, ellp    */
+    GPRN_OP_COS = 10,  /* theta, P                       */
+    GPRN_OP_EXP = 11,  /* theta, ell                     */
     GPRN_OP_ADD = 100,
     GPRN_OP_MUL = 101
 };

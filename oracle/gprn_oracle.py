@@ -19,6 +19,7 @@ All citations ``file:line`` are relative to the reference checkout (``/root/refe
 Kernel specification used throughout (a tiny expression tree, no reference classes needed):
     ("SE", theta, ell) | ("P", theta, P, ell) | ("QP", theta, elle, P, ellp) |
     ("RQ", theta, alpha, ell) | ("M32", theta, ell) | ("M52", theta, ell) | ("WN", w) |
+    ("C", c) | ("RQP", theta, alpha, elle, P, ellp) | ("COS", theta, P) | ("EXP", theta, ell) |
     ("sum", spec1, spec2) | ("mul", spec1, spec2)
 """
 from __future__ import annotations
@@ -57,6 +58,15 @@ def kernel_eval(spec, r):
         ar = np.abs(r)
         return a[0] ** 2 * (1.0 + (3 * np.sqrt(5) * a[1] * ar + 5 * ar ** 2) / (3 * a[1] ** 2)) \
             * np.exp(-np.sqrt(5.0) * ar / a[1])
+    if tag == "C":                        # covfunc.py:122-125
+        return np.full_like(r, a[0] ** 2)
+    if tag == "RQP":                      # covfunc.py:307-310
+        return a[0] ** 2 * np.exp(-2 * np.sin(np.pi * np.abs(r) / a[3]) ** 2 / a[4] ** 2) \
+            * (1 + r ** 2 / (2 * a[1] * a[2] ** 2)) ** (-a[1])
+    if tag == "COS":                      # covfunc.py:327-328
+        return a[0] ** 2 * np.cos(2 * np.pi * np.abs(r) / a[1])
+    if tag == "EXP":                      # covfunc.py:351-352
+        return a[0] ** 2 * np.exp(-np.abs(r) / a[1])
     if tag == "WN":                       # covfunc.py:144-148 (quirk Q9: decided by shape, not by r==0)
         if r.ndim == 2 and r.shape[0] == r.shape[1]:
             return a[0] ** 2 * np.eye(r.shape[0])

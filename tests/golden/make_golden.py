@@ -55,7 +55,8 @@ from gpyrn import covfunc, meanfunc, meanfield  # noqa: E402  (the reference its
 
 KCLS = {"SE": covfunc.SquaredExponential, "P": covfunc.Periodic, "QP": covfunc.QuasiPeriodic,
         "RQ": covfunc.RationalQuadratic, "M32": covfunc.Matern32, "M52": covfunc.Matern52,
-        "WN": covfunc.WhiteNoise}
+        "WN": covfunc.WhiteNoise, "C": covfunc.Constant, "RQP": covfunc.RQP, "COS": covfunc.Cosine,
+        "EXP": covfunc.Exponential}
 
 
 def build_kernel(spec):
@@ -131,7 +132,9 @@ def kernel_vectors():
     specs = [("SE", 1.3, 11.0), ("P", 0.9, 17.0, 0.8), ("QP", 1.1, 35.0, 23.0, 0.6), ("RQ", 1.2, 0.7, 9.0),
              ("M32", 0.8, 14.0), ("M52", 1.4, 21.0), ("WN", 0.3),
              ("sum", ("SE", 1.0, 10.0), ("WN", 0.2)), ("mul", ("SE", 1.0, 10.0), ("P", 1.0, 20.0, 0.5)),
-             ("sum", ("mul", ("M52", 1.1, 30.0), ("P", 1.0, 12.0, 0.9)), ("RQ", 0.5, 1.5, 40.0))]
+             ("sum", ("mul", ("M52", 1.1, 30.0), ("P", 1.0, 12.0, 0.9)), ("RQ", 0.5, 1.5, 40.0)),
+             ("C", 0.7), ("RQP", 1.2, 0.8, 33.0, 19.0, 0.9), ("COS", 0.9, 14.0), ("EXP", 1.1, 25.0),
+             ("sum", ("mul", ("EXP", 1.0, 50.0), ("COS", 1.0, 9.0)), ("C", 0.1))]
     out = dict(t=t, tstar=ts, specs=np.array([repr(s) for s in specs]))
     for i, s in enumerate(specs):
         k = build_kernel(s)
@@ -206,6 +209,11 @@ def main():
              [("RQ", 1.0, 0.9, 60.0), ("M52", 1.1, 90.0), ("mul", ("P", 0.9, 33.0, 1.1), ("M32", 1.0, 120.0)),
               ("SE", 1.2, 75.0)],
              [0.1, -0.2], [0.12, 0.08], tstar=np.linspace(t[0], t[-1] + 10, 45))
+    # the four "next" kernels through the whole ELBO / prediction path
+    t, ys, es = synth_data(70, 2, seed=9)
+    run_case("next_kernels_70_2_1", t, ys, es, [("sum", ("RQP", 1.0, 1.2, 80.0, 25.0, 0.9), ("C", 0.2))],
+             [("EXP", 1.1, 150.0), ("sum", ("mul", ("SE", 1.0, 90.0), ("COS", 1.0, 400.0)), ("WN", 0.02))],
+             [0.0, 0.1], [0.1, 0.1], tstar=np.linspace(t[0], t[-1], 33))
 
 
 if __name__ == "__main__":

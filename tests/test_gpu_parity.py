@@ -20,7 +20,8 @@ pytestmark = pytest.mark.gpu
 
 KCLS = {"SE": covfunc.SquaredExponential, "P": covfunc.Periodic, "QP": covfunc.QuasiPeriodic,
         "RQ": covfunc.RationalQuadratic, "M32": covfunc.Matern32, "M52": covfunc.Matern52,
-        "WN": covfunc.WhiteNoise}
+        "WN": covfunc.WhiteNoise, "C": covfunc.Constant, "RQP": covfunc.RQP, "COS": covfunc.Cosine,
+        "EXP": covfunc.Exponential}
 
 
 def build_kernel(spec):
@@ -68,10 +69,12 @@ def test_kernel_matrices_match_reference():
     g = gp.inference(1, t, np.zeros_like(t), np.ones_like(t))
     for i, s in enumerate(z["specs"]):
         k = build_kernel(ast.literal_eval(str(s)))
-        np.testing.assert_allclose(g._kmat(k, t, None, 0.0), z[f"Ksq_{i}"], rtol=1e-13, atol=1e-300)
-        np.testing.assert_allclose(g._predictKMatrix(k, ts), z[f"Krect_{i}"], rtol=1e-13, atol=1e-300)
-        np.testing.assert_allclose(k(t[:, None] - t[None, :]), z[f"Ksq_{i}"], rtol=1e-13, atol=1e-300)
-        np.testing.assert_allclose(g._KMatrix(k), z[f"Ksq_{i}"] + 1e-6 * np.eye(t.size), rtol=1e-13, atol=1e-300)
+        # relative 1e-13; absolute floor 2e-15 of the amplitude for kernels that cross zero (Cosine)
+        tol = dict(rtol=1e-13, atol=2e-15 * np.max(np.abs(z[f"Ksq_{i}"])))
+        np.testing.assert_allclose(g._kmat(k, t, None, 0.0), z[f"Ksq_{i}"], **tol)
+        np.testing.assert_allclose(g._predictKMatrix(k, ts), z[f"Krect_{i}"], **tol)
+        np.testing.assert_allclose(k(t[:, None] - t[None, :]), z[f"Ksq_{i}"], **tol)
+        np.testing.assert_allclose(g._KMatrix(k), z[f"Ksq_{i}"] + 1e-6 * np.eye(t.size), **tol)
 
 
 def test_QP_equals_prod():
@@ -249,6 +252,27 @@ def test_batch_with_per_set_means():
         mb.mean_vals = np.repeat(P[b, nk:nk + 2][:, None], m.N, axis=1)
         e, *_ = orc.elbo_calc(mb)
         assert abs(elbo[b] - e) <= 1e-10 * abs(e)
+
+
+def test_batch_warm_start_state_roundtrip():
+    """Row (f.1): batched warm start.  Stopping a batch after 3 iterations and resuming it from the returned
+    state must land on the same fixed point as the oracle resumed from the same state (meanfield.py:598-607)."""
+    m = orc.synth(64, 2, 1, seed=6, node="QP")
+    theta = orc.perturbed_hyper_sets(m, 5, 21)
+    g = from_oracle_model(m)
+    P = full_parameters(m, theta)
+    e3, it3, st3, mu3, var3 = g.ELBO_batch(P, max_iter=3, return_info=True, return_state=True)
+    assert np.all(it3 == 3) and np.all(st3 == 2) and mu3.shape == (5, g.d)
+    e, it, st, mu, var = g.ELBO_batch(P, return_info=True, mu=mu3, var=var3, return_state=True)
+    for b in range(5):
+        mb = orc.model_with_hyper(m, theta[b])
+        _, mu_o, var_o, _ = orc.elbo_calc(mb, max_iter=3)
+        e_o, mu_f, var_f, it_o = orc.elbo_calc(mb, mu=mu_o, var=var_o)
+        assert it[b] == it_o and st[b] == 0
+        assert abs(e[b] - e_o) <= 1e-10 * abs(e_o)
+        assert rel(mu[b], np.asarray(mu_f).ravel()) < 1e-8
+    with pytest.raises(ValueError):
+        g.ELBO_batch(P, mu=mu3)
 
 
 def test_c3_full_size_properties():

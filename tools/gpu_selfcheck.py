@@ -23,7 +23,8 @@ from tests._cases import GOLDEN, golden_names, load_golden  # noqa: E402
 
 KCLS = {"SE": covfunc.SquaredExponential, "P": covfunc.Periodic, "QP": covfunc.QuasiPeriodic,
         "RQ": covfunc.RationalQuadratic, "M32": covfunc.Matern32, "M52": covfunc.Matern52,
-        "WN": covfunc.WhiteNoise}
+        "WN": covfunc.WhiteNoise, "C": covfunc.Constant, "RQP": covfunc.RQP, "COS": covfunc.Cosine,
+        "EXP": covfunc.Exponential}
 fails = []
 
 
