@@ -131,11 +131,18 @@ def cpu_sample(wname, w, budget_s=30.0, iters_hint=None):
         t0 = time.perf_counter()
         orc.elbo_aux(mb, Kf, Kw, Lf, Lw, mb.y - mb.mean_vals, mb.jitters ** 2, mu, var)
         t_aux = time.perf_counter() - t0
-        n_it = iters_hint if iters_hint else 60
+        src = "iteration count of this set from the GPU run beside it"
+        if not iters_hint:
+            try:    # counts recorded by tools/record_iterations.py on a B200 (parity tests: counts equal the reference's)
+                iters_hint = int(json.load(open(os.path.join(ROOT, "profiles", f"iterations_{wname}.json")))["iterations"][0])
+                src = f"iteration count of this set recorded in profiles/iterations_{wname}.json"
+            except Exception:
+                iters_hint, src = 50, "iteration count assumed"
+        n_it = iters_hint
         per_eval = t_setup + (n_it + 1) * t_aux
         return {"value": 1.0 / per_eval, "unit": "elbo_evals/s", "cores": cores, "kind": "port",
                 "sample": f"1 set: setup {t_setup:.1f} s + 1 ELBOaux iteration {t_aux:.1f} s measured; evaluation = setup + "
-                          f"(n_it+1) iterations with n_it={n_it} ({'GPU count for this set' if iters_hint else 'assumed'}); "
+                          f"(n_it+1) iterations with n_it={n_it} ({src}); "
                           f"numpy/scipy oracle port of the reference algorithm, OpenBLAS threads={cores}",
                 "seconds": time.perf_counter() - t_start}
     done, its = 0, 0
