@@ -210,8 +210,25 @@ def run_ours(args, w):
     N, p, q = w["N"], w["p"], w["q"]
     B_local = args.sets_per_gpu or w["sets_per_gpu"]
     B = B_local * world
-    theta = workloads.perturbed_sets(th0, B, w["seed"])
-    idx = D.shard_indices(B, world, rank, "strided")
+    # Equal-work shards: the sets differ a lot in cost (C4: 34...94 iterations), so a fair weak-scaling series needs
+    # per-GPU work that does not depend on N.  With recorded iteration counts (profiles/iterations_<w>.json, written by
+    # tools/record_iterations.py) the pool of 8 x sets_per_gpu sets is cut into 8 blocks of equal summed cost; rank r
+    # always evaluates block r, whatever N is.  Without the record: round-robin shards, re-dealt after the warm-up.
+    pool_B = B_local * max(8, world)
+    theta = workloads.perturbed_sets(th0, pool_B, w["seed"])
+    blocks = None
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", f"iterations_{args.workload}.json")))["iterations"]
+        if len(rec) >= pool_B and not args.no_balance:
+            blocks = D.balanced_assignment(rec[:pool_B], pool_B // B_local)
+    except Exception:
+        blocks = None
+    if blocks is not None:
+        idx = blocks[rank]
+        used = np.sort(np.concatenate(blocks[:world]))
+    else:
+        idx = D.shard_indices(B, world, rank, "strided")
+        used = np.arange(B)
     theta_l = np.ascontiguousarray(theta[idx])
     KC = {"QP": covfunc.QuasiPeriodic, "M52": covfunc.Matern52, "SE": covfunc.SquaredExponential}
     ya = []
@@ -245,11 +262,11 @@ def run_ours(args, w):
     for _ in range(args.warmup):
         step_dev()
     barrier()
-    if world > 1 and not args.no_balance:
+    if world > 1 and blocks is None and not args.no_balance:
         # re-deal the sets so that every rank carries the same summed iteration count (measured by the warm-up
         # pass); counts per rank stay equal, so this is still weak scaling over the same global batch
-        it_all = D.gather_results(idx, {"iters": d_iters.cpu().numpy().astype(np.int64)}, B)["iters"]
-        idx = D.balanced_assignment(it_all, world)[rank]
+        it_all = D.gather_results(idx, {"iters": d_iters.cpu().numpy().astype(np.int64)}, pool_B)["iters"]
+        idx = used[D.balanced_assignment(it_all[used], world)[rank]]
         theta_l = np.ascontiguousarray(theta[idx])
         P_l = np.concatenate([theta_l[:, :-p], np.zeros((B_local, p)), theta_l[:, -p:]], axis=1)
         d_hyper.copy_(torch.from_numpy(theta_l))
@@ -292,8 +309,8 @@ def run_ours(args, w):
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(fl, op=dist.ReduceOp.SUM)
         # the one collective of the path: gather the ELBO values (NCCL over NVLink)
-        res = D.gather_results(idx, {"elbo": elbo_l, "iters": iters_l}, B)
-        elbo_all = res["elbo"]
+        res = D.gather_results(idx, {"elbo": elbo_l, "iters": iters_l}, pool_B)
+        elbo_all = res["elbo"][used]
     else:
         elbo_all = elbo_l
     if rank == 0:
@@ -308,7 +325,9 @@ def run_ours(args, w):
                "config": {"workload": w["name"], "N": N, "p": p, "q": q, "sets_per_gpu": B_local, "global_sets": B,
                           "mean_iterations": iters_step / B, "elbo_iterations_per_sec": iters_step * args.steps / (ms_tot * 1e-3),
                           "not_converged_or_failed": int(bad),
-                          "sharding": "round-robin" if (world == 1 or args.no_balance) else "round-robin, re-dealt by warm-up iteration counts (equal sets per rank)",
+                          "sharding": ("equal-cost blocks from recorded iteration counts (profiles/iterations_%s.json); rank r always evaluates block r" % args.workload)
+                          if blocks is not None else ("round-robin" if (world == 1 or args.no_balance) else
+                                                      "round-robin, re-dealt by warm-up iteration counts (equal sets per rank)"),
                           "l2": "256 MiB flush between steps; per-step working set (K, L, L^-1 per matrix) >> 126 MB L2",
                           "elbo_checksum": float(np.sum(elbo_all))},
                "e2e": {"value": B * args.steps / (e2e_ms * 1e-3), "unit": "elbo_evals/s",
@@ -319,7 +338,7 @@ def run_ours(args, w):
                             "what": "whole batched evaluation, algorithmic FP64 flops (SURVEY.md 8d) / device time, per GPU"},
                "clocks": clocks}
         if world == 1 and not args.no_cpu:
-            hint = int(iters_l[0]) if N >= 1024 else None
+            hint = int(iters_l[0]) if (N >= 1024 and blocks is None) else None   # set 0 is what the CPU leg times
             cb = cpu_sample(args.workload, w, budget_s=20.0, iters_hint=hint)
             cb.pop("seconds", None)
             out["cpu_baseline"] = cb
