@@ -221,6 +221,9 @@ def run_ours(args, w):
         rec = json.load(open(os.path.join(ROOT, "profiles", f"iterations_{args.workload}.json")))["iterations"]
         if len(rec) >= pool_B and not args.no_balance:
             blocks = D.balanced_assignment(rec[:pool_B], pool_B // B_local)
+            # blocks have (nearly) equal summed cost; order them by their longest evaluation so that block 0 -- the
+            # N = 1 workload -- is the one with the shortest straggler tail, and larger N add the longer-tailed ones
+            blocks.sort(key=lambda b: (max(rec[i] for i in b), sum(rec[i] for i in b)))
     except Exception:
         blocks = None
     if blocks is not None:
