@@ -60,7 +60,8 @@ def build_library(verbose=False):
     """Compile gpyrn_b200/csrc/gprn_api.cu -> libgprn_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
     src = os.path.join(CSRC, "gprn_api.cu")
     out = os.path.join(CSRC, "libgprn_b200.so")
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", out, src]
+    extra = os.environ.get("GPRN_NVCC_EXTRA", "").split()
+    cmd = ["nvcc"] + NVCC_FLAGS + extra + ["-o", out, src]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True, cwd=CSRC)

@@ -15,7 +15,10 @@ namespace gprn {
 
 #define G_BM 128
 #define G_BN 128
+#ifndef G_BK
 #define G_BK 16
+#endif
+#define G_KCH (G_BK / 2)            // 16-byte chunks per operand row and k-slab
 #ifndef G_THREADS
 #define G_THREADS 512             // 16 warps, 4 (M) x 4 (N), 32x32 accumulator tile per warp
 #endif
@@ -26,8 +29,8 @@ namespace gprn {
 #ifndef G_STAGES
 #define G_STAGES 4
 #endif
-#define G_LDA 20                    // As[m][k]
-#define G_LDB_NT 20                 // Bs[n][k]
+#define G_LDA (G_BK + 4)            // As[m][k]; (BK+4)*8 B = 32 (mod 128) for BK = 16, 32
+#define G_LDB_NT (G_BK + 4)         // Bs[n][k]
 #define G_LDB_NN 132                // Bs[k][n]
 #define G_A_STAGE (G_BM * G_LDA)    // doubles
 #define G_B_STAGE_NT (G_BN * G_LDB_NT)
@@ -48,19 +51,19 @@ __device__ __forceinline__ void gemm128_load_stage(double* As, double* Bs, const
                                                    const double* __restrict__ B, size_t ldb, int k0, int tid) {
     // A: 128 rows x 8 chunks of 2 doubles
 #pragma unroll
-    for (int u = 0; u < 1024 / G_THREADS; u++) {
-        int ch = tid + G_THREADS * u, row = ch >> 3, kc = ch & 7;
+    for (int u = 0; u < G_BM * G_KCH / G_THREADS; u++) {
+        int ch = tid + G_THREADS * u, row = ch / G_KCH, kc = ch % G_KCH;
         cp_async16(As + row * G_LDA + 2 * kc, A + (size_t)row * lda + k0 + 2 * kc);
     }
     if (!B_KMAJOR) {
 #pragma unroll
-        for (int u = 0; u < 1024 / G_THREADS; u++) {
-            int ch = tid + G_THREADS * u, row = ch >> 3, kc = ch & 7;
+        for (int u = 0; u < G_BN * G_KCH / G_THREADS; u++) {
+            int ch = tid + G_THREADS * u, row = ch / G_KCH, kc = ch % G_KCH;
             cp_async16(Bs + row * G_LDB_NT + 2 * kc, B + (size_t)row * ldb + k0 + 2 * kc);
         }
     } else {
 #pragma unroll
-        for (int u = 0; u < 1024 / G_THREADS; u++) {
+        for (int u = 0; u < G_BK * 64 / G_THREADS; u++) {
             int ch = tid + G_THREADS * u, k = ch >> 6, nc = ch & 63;
             cp_async16(Bs + k * G_LDB_NN + 2 * nc, B + (size_t)(k0 + k) * ldb + 2 * nc);
         }
