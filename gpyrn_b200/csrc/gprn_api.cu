@@ -29,11 +29,28 @@ static int fail(const std::string& msg) { g_err = msg; return 1; }
                         std::to_string(__LINE__) + ")");                                                \
     } while (0)
 static const bool g_debug_sync = getenv("GPRN_DEBUG_SYNC") != nullptr;   // serialise launches to localise a fault
+// GPRN_PROFILE=1: synchronise after every launch and attribute the host wall time since the previous launch check
+// to the source line of the launch (development aid; dumped to stderr by gprn_destroy).
+static const bool g_profile = getenv("GPRN_PROFILE") != nullptr;
+#include <chrono>
+#include <map>
+static std::map<int, std::pair<double, long>> g_prof;
+static std::chrono::steady_clock::time_point g_prof_last;
+static void prof_tick(int line) {
+    cudaDeviceSynchronize();
+    auto now = std::chrono::steady_clock::now();
+    double us = std::chrono::duration<double, std::micro>(now - g_prof_last).count();
+    auto& e = g_prof[line];
+    e.first += us;
+    e.second += 1;
+    g_prof_last = std::chrono::steady_clock::now();
+}
 #define LAUNCH_CHECK(h)                                                                                 \
     do {                                                                                                \
         (h)->launches++;                                                                                \
         cudaError_t e_ = cudaGetLastError();                                                            \
         if (e_ == cudaSuccess && g_debug_sync) e_ = cudaDeviceSynchronize();                            \
+        if (g_profile) prof_tick(__LINE__);                                                             \
         if (e_ != cudaSuccess)                                                                          \
             return fail(std::string("kernel launch: ") + cudaGetErrorString(e_) + " (" + __FILE__ +     \
                         ":" + std::to_string(__LINE__) + ")");                                          \
@@ -187,6 +204,14 @@ extern "C" int gprn_create(int device, int N, int p, int q, const double* time, 
 
 extern "C" int gprn_destroy(gprn_handle* h) {
     if (!h) return 0;
+    if (g_profile) {
+        double tot = 0;
+        for (auto& kv : g_prof) tot += kv.second.first;
+        for (auto& kv : g_prof)
+            fprintf(stderr, "[gprn profile] line %4d: %9.1f ms  %7ld launches  %5.1f %%\n", kv.first, kv.second.first * 1e-3,
+                    kv.second.second, 100.0 * kv.second.first / tot);
+        g_prof.clear();
+    }
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : h->all)
