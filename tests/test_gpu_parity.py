@@ -204,6 +204,22 @@ def test_previous_warm_start_and_nelbo(capsys):
         g.ELBOcalc(mu='bogus', var='bogus')
 
 
+def test_optimize_and_predict_drivers(capsys):
+    """The host drivers above the path (reference meanfield.py:1114-1152 optimize, :1381-1400 predict) run unchanged
+    against the device path: Nelder-Mead over one free parameter improves the ELBO; predict() returns the 4-tuple."""
+    d = load_golden("synth_50_1_1_QP")
+    g = from_golden(d)
+    e0 = g.ELBO
+    res = g.optimize(vars='node1.P', options={'maxfev': 12, 'xatol': 1e-3})
+    assert res.x.shape == (1,) and g.frozen_mask.sum() == g.n_parameters - 1
+    assert -res.fun >= e0 - 1e-9 * abs(e0)
+    assert g.nodes[0].pars[2] == res.x[0]
+    tstar, mean, std, sep = g.predict(nn=37)
+    assert tstar.shape == (37,) and mean.shape == std.shape == (37, 1) and np.all(np.isfinite(std))
+    assert sep[0].shape == (1, 37) and sep[1].shape == (1, 37)
+    capsys.readouterr()
+
+
 def test_not_positive_definite_reports_nan():
     t = np.linspace(0, 1, 20)
     y, e = np.sin(t), np.full(20, 0.1)
