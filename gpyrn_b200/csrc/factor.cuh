@@ -296,13 +296,33 @@ __global__ void __launch_bounds__(G_THREADS) syrk_outer_kernel(double* __restric
 
 // Inverse, block row of 256 rows starting at R0: X[rows, 0:R0] = - L[rows, n0:R0] X[n0:R0, cols] (the part of
 // the row-sweep sum that lies above the block), 128x128 tiles.  X must hold zeros in its upper tiles.
-// grid = (2 * R0/128, nmat), block = G_THREADS, dynamic smem GEMM128_SMEM.
+// The K range of a tile, R0 - n0, shrinks with its column, which leaves most SMs idle behind the few long tiles
+// when few matrices are in flight.  The host can therefore cut the range into chunks of kc (>= TRTRI_KC): chunk 0
+// writes to X as before, chunk s >= 1 to the partial buffer Gp[id][s-1] (256 x Np strip, same row/column indexing);
+// the in-block kernel adds the partials in a fixed order (deterministic, no atomics).  With enough matrices in
+// flight the launch is already full and kc = R0 (no split) is faster: shorter K means more prologue / epilogue.
+// grid = (2 * trtri_outer_units(R0), nmat), block = G_THREADS, dynamic smem GEMM128_SMEM.
+#define TRTRI_KC 1024
+#define TRTRI_MAXCH(Np) (((Np) + TRTRI_KC - 1) / TRTRI_KC)      // chunks of the longest tile
+__host__ __device__ __forceinline__ int trtri_nchunk(int R0, int n0, int kc) { return (R0 - n0 + kc - 1) / kc; }
+__host__ __forceinline__ int trtri_outer_units(int R0, int kc) {
+    int u = 0;
+    for (int n0 = 0; n0 < R0; n0 += G_BN) u += trtri_nchunk(R0, n0, kc);
+    return u;
+}
 __global__ void __launch_bounds__(G_THREADS) trtri_outer_kernel(double* __restrict__ X, const double* __restrict__ W,
-                                                          const int* __restrict__ ids, int Np, int R0) {
+                                                                double* __restrict__ Gp, const int* __restrict__ ids,
+                                                                int Np, int R0, int units, int kc) {
     extern __shared__ double smem[];
-    const int ncol = R0 / G_BN;
-    const int TJ = blockIdx.x % ncol, half = blockIdx.x / ncol;
-    const int r0 = R0 + half * G_BM, n0 = TJ * G_BN;
+    const int half = blockIdx.x / units;
+    int u = blockIdx.x % units, n0 = 0, s = 0;
+    for (;; n0 += G_BN) {                      // decode (column tile, chunk)
+        const int nc = trtri_nchunk(R0, n0, kc);
+        if (u < nc) { s = u; break; }
+        u -= nc;
+    }
+    const int r0 = R0 + half * G_BM;
+    const int k0 = n0 + s * kc, k1 = min(k0 + kc, R0);
     const int id = ids[blockIdx.y];
     const double* Wm = W + (size_t)id * Np * Np;
     double* Xm = X + (size_t)id * Np * Np;
@@ -311,10 +331,11 @@ __global__ void __launch_bounds__(G_THREADS) trtri_outer_kernel(double* __restri
     for (int i = 0; i < G_MI; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    gemm128_mainloop<true>(acc, smem, Wm + (size_t)r0 * Np + n0, Np, Xm + (size_t)n0 * Np + n0, Np, R0 - n0);
+    gemm128_mainloop<true>(acc, smem, Wm + (size_t)r0 * Np + k0, Np, Xm + (size_t)k0 * Np + n0, Np, k1 - k0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3;
     const int r = lane >> 2, c = lane & 3;
-    double* C = Xm + (size_t)r0 * Np + n0;
+    double* C = (s == 0) ? Xm + (size_t)r0 * Np + n0
+                         : Gp + ((size_t)id * (TRTRI_MAXCH(Np) - 1) + (s - 1)) * OUTER_KB * Np + (size_t)(half * G_BM) * Np + n0;
 #pragma unroll
     for (int i = 0; i < G_MI; i++)
 #pragma unroll
@@ -329,7 +350,8 @@ __global__ void __launch_bounds__(G_THREADS) trtri_outer_kernel(double* __restri
 // sum left in place by trtri_outer_kernel (zero for columns inside the block).  grid = (min(i0+4, nt) - 1, nmat),
 // block = 128, dynamic smem TRTRI_SMEM.
 __global__ void __launch_bounds__(128) trtri_inblock_kernel(double* __restrict__ X, const double* __restrict__ W,
-                                                            const int* __restrict__ ids, int Np, int i0) {
+                                                            const double* __restrict__ Gp, const int* __restrict__ ids,
+                                                            int Np, int i0, int kc) {
     extern __shared__ double smem[];
     double* As = smem;
     double* Bs = smem + NB * LDT;
@@ -354,6 +376,20 @@ __global__ void __launch_bounds__(128) trtri_inblock_kernel(double* __restrict__
                     acc[a][b][0] = v.x;
                     acc[a][b][1] = v.y;
                 }
+            // split-K partials of trtri_outer_kernel, added in chunk order
+            const int nch = Gp ? trtri_nchunk(i0 * NB, (j >> 1) * G_BN, kc) : 1;
+            for (int sp = 1; sp < nch; sp++) {
+                const double* gp = Gp + ((size_t)id * (TRTRI_MAXCH(Np) - 1) + (sp - 1)) * OUTER_KB * Np +
+                                   (size_t)((i - i0) * NB) * Np + j * NB;
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        double2 v = *reinterpret_cast<const double2*>(gp + (size_t)(wm * 32 + a * 8 + r) * Np + wn * 32 + b * 8 + 2 * c);
+                        acc[a][b][0] += v.x;
+                        acc[a][b][1] += v.y;
+                    }
+            }
         } else {
 #pragma unroll
             for (int a = 0; a < 4; a++)

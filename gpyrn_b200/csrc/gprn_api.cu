@@ -80,7 +80,7 @@ struct gprn_handle {
     std::vector<int32_t> h_tok, h_len, h_par_off, h_npar;
     // workspace (grow only)
     std::vector<DevBuf*> all;
-    DevBuf K, W, X, XK, vecs, state, small, lists, hyper, ysub, ks, pred, scratch;
+    DevBuf K, W, X, XK, vecs, state, small, lists, hyper, ysub, ks, pred, scratch, gpart;
     int num_sms = 148;
     // pinned staging
     int* h_lists = nullptr;
@@ -197,7 +197,7 @@ extern "C" int gprn_create(int device, int N, int p, int q, const double* time, 
     CU(cudaMemcpy(h->d_yerr2, e2.data(), sizeof(double) * p * N, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_ysub_shared, y, sizeof(double) * p * N, cudaMemcpyHostToDevice));
     CU(cudaDeviceSynchronize());   // pageable-memory copies above must have landed before any non-blocking stream runs
-    h->all = {&h->K, &h->W, &h->X, &h->XK, &h->vecs, &h->state, &h->small, &h->lists, &h->hyper, &h->ysub, &h->ks, &h->pred, &h->scratch};
+    h->all = {&h->K, &h->W, &h->X, &h->XK, &h->vecs, &h->state, &h->small, &h->lists, &h->hyper, &h->ysub, &h->ks, &h->pred, &h->scratch, &h->gpart};
     *out = h;
     return 0;
 }
@@ -318,7 +318,9 @@ extern "C" int gprn_set_model(gprn_handle* h, const int32_t* node_prog, const in
 // ------------------------------------------------------------------------------------------------
 static int factor_batch(gprn_handle* h, double* W, const int* d_ids, int nmat, double* logdet, int* mstatus,
                         int* ctr /* per-matrix tickets, zero between launches */, double* X /* null: no inverse */,
-                        cudaStream_t st) {
+                        cudaStream_t st, int nmat_concurrent = 0 /* matrices in flight on all streams */) {
+    if (nmat_concurrent < nmat) nmat_concurrent = nmat;
+    double* Gp = (double*)h->gpart.p;     // split-K partials of the inverse (two-level path), indexed by matrix id
     const int nt = h->nt, Np = h->Np;
     const bool two = use_two_level(Np);
     // Cholesky: panels of 4 tile columns, left-looking inside the panel, right-looking trailing update per panel
@@ -345,13 +347,18 @@ static int factor_batch(gprn_handle* h, double* W, const int* d_ids, int nmat, d
         LAUNCH_CHECK(h);
         if (two || nt <= 4) {
             for (int i0 = 0; i0 < nt; i0 += 4) {
+                int kc = TRTRI_KC;
                 if (i0 > 0) {
-                    trtri_outer_kernel<<<dim3(2 * (i0 * NB / G_BN), nmat), G_THREADS, GEMM128_SMEM, st>>>(X, W, d_ids, Np, i0 * NB);
+                    // split the K range only while the launch would leave SMs idle (few matrices in flight)
+                    static const bool no_split = getenv("GPRN_NO_SPLITK") != nullptr;
+                    kc = (no_split || nmat_concurrent * 2 * (i0 * NB / G_BN) >= 2 * h->num_sms) ? std::max(i0 * NB, TRTRI_KC) : TRTRI_KC;
+                    const int units = trtri_outer_units(i0 * NB, kc);
+                    trtri_outer_kernel<<<dim3(2 * units, nmat), G_THREADS, GEMM128_SMEM, st>>>(X, W, Gp, d_ids, Np, i0 * NB, units, kc);
                     LAUNCH_CHECK(h);
                 }
                 const int ncol = std::min(i0 + 4, nt) - 1;
                 if (ncol > 0) {
-                    trtri_inblock_kernel<<<dim3(ncol, nmat), 128, TRTRI_SMEM, st>>>(X, W, d_ids, Np, i0);
+                    trtri_inblock_kernel<<<dim3(ncol, nmat), 128, TRTRI_SMEM, st>>>(X, W, two ? Gp : nullptr, d_ids, Np, i0, kc);
                     LAUNCH_CHECK(h);
                 }
             }
@@ -379,7 +386,7 @@ static int factor_batch_multi(gprn_handle* h, double* W, const int* d_ids, int n
     for (int g = 0; g < G; g++) {
         const int len = nmat / G + (g < nmat % G ? 1 : 0);
         CU(cudaStreamWaitEvent(h->aux[g], h->ev_fork, 0));
-        if (factor_batch(h, W, d_ids + start, len, logdet, mstatus, ctr, X, h->aux[g])) return 1;
+        if (factor_batch(h, W, d_ids + start, len, logdet, mstatus, ctr, X, h->aux[g], nmat)) return 1;
         CU(cudaEventRecord(h->ev_join[g], h->aux[g]));
         CU(cudaStreamWaitEvent(st, h->ev_join[g], 0));
         start += len;
@@ -425,6 +432,8 @@ static size_t per_set_bytes(const gprn_handle* h) {
     size_t vecs = 8 * M * Np * sizeof(double);
     size_t state = 4 * (size_t)h->d * sizeof(double);
     size_t misc = (size_t)h->H * 8 + (size_t)h->p * h->N * 8 + 4096;
+    if (!use_small_path(h) && use_two_level(h->Np))
+        misc += M * (size_t)(TRTRI_MAXCH(h->Np) - 1) * OUTER_KB * Np * sizeof(double);      // split-K partials of the inverse
     return mats + vecs + state + misc;
 }
 
@@ -440,6 +449,8 @@ static int setup_chunk(gprn_handle* h, int nset, Chunk& ck, bool ysub_per_set, b
         // the inverse factors must hold zeros in their (never written) upper tiles: trtri_outer_kernel reads them
         if (ensure_zeroed(h->X, matbytes)) return 1;
         if (h->q > 1 && ensure_zeroed(h->XK, matbytes)) return 1;
+        if (use_two_level(h->Np) && TRTRI_MAXCH(h->Np) > 1 &&
+            ensure(h->gpart, (size_t)nset * M * (TRTRI_MAXCH(h->Np) - 1) * OUTER_KB * Np * sizeof(double))) return 1;
     }
     const size_t ve = (size_t)nset * M * Np;
     if (ensure(h->vecs, 7 * ve * sizeof(double))) return 1;
@@ -788,6 +799,8 @@ extern "C" int gprn_debug_factor(gprn_handle* h, int n, const double* A, double*
     CU(cudaMemsetAsync(dids, 0, sizeof(int), st));
     CU(cudaMemsetAsync(dst, 0, sizeof(int), st));
     CU(cudaMemsetAsync(dctr, 0, sizeof(int), st));
+    if (use_two_level(Np) && TRTRI_MAXCH(Np) > 1 &&
+        ensure(h->gpart, (size_t)(TRTRI_MAXCH(Np) - 1) * OUTER_KB * Np * sizeof(double))) return 1;
     gprn_handle tmp = *h;          // borrow counters / geometry for the driver
     tmp.Np = Np;
     tmp.nt = Np / NB;
