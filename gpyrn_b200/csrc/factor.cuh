@@ -258,15 +258,23 @@ __global__ void __launch_bounds__(128) trtri_row_kernel(double* __restrict__ X, 
 // ------------------------------------------------------------------------------------------------
 #define OUTER_KB 256
 
-// Trailing update after the 256-column panel starting at column c0: for 128x128 tiles (TI >= TJ) of the
-// trailing square starting at t0 = c0 + 256:  C -= L[rows, c0:c0+256] L[cols, c0:c0+256]^T.
-// grid = (n(n+1)/2 with n = (Np - t0)/128, nmat), block = G_THREADS, dynamic smem GEMM128_SMEM.
+// Trailing update with the K-slab of columns [c0, c0 + KB): for 128x128 tiles (TI >= TJ) of the trailing square that
+// starts at column t0,  C -= L[rows, c0:c0+KB] L[cols, c0:c0+KB]^T.  jcols = 0: all tiles; jcols = 2: only the first
+// two tile columns (the next 256-column panel).  The host applies slabs lazily -- after an even panel only the next
+// panel's columns are updated (KB = 256), after an odd panel everything to the right gets both slabs at once
+// (KB = 512) -- which halves the read-modify-write passes over the trailing matrix.
+// grid = (tiles, nmat), block = G_THREADS, dynamic smem GEMM128_SMEM.
 __global__ void __launch_bounds__(G_THREADS) syrk_outer_kernel(double* __restrict__ W, const int* __restrict__ ids,
-                                                               int Np, int c0) {
+                                                               int Np, int c0, int KB, int t0, int jcols) {
     extern __shared__ double smem[];
     int TI, TJ;
-    tri_decode(blockIdx.x, TI, TJ);
-    const int t0 = c0 + OUTER_KB;
+    if (jcols == 0) {
+        tri_decode(blockIdx.x, TI, TJ);
+    } else {
+        const int n128 = (Np - t0) / G_BM;
+        if ((int)blockIdx.x < n128) { TI = blockIdx.x; TJ = 0; }
+        else { TI = blockIdx.x - n128 + 1; TJ = 1; }
+    }
     const int r0 = t0 + TI * G_BM, n0 = t0 + TJ * G_BN;
     const int id = ids[blockIdx.y];
     double* Wm = W + (size_t)id * Np * Np;
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__(G_THREADS) syrk_outer_kernel(double* __restric
     for (int i = 0; i < G_MI; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    gemm128_mainloop<false>(acc, smem, Wm + (size_t)r0 * Np + c0, Np, Wm + (size_t)n0 * Np + c0, Np, OUTER_KB);
+    gemm128_mainloop<false>(acc, smem, Wm + (size_t)r0 * Np + c0, Np, Wm + (size_t)n0 * Np + c0, Np, KB);
 #pragma unroll
     for (int i = 0; i < G_MI; i++)
 #pragma unroll

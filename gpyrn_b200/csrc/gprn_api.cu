@@ -333,8 +333,16 @@ static int factor_batch(gprn_handle* h, double* W, const int* d_ids, int nmat, d
         }
         if (ke < nt) {
             if (two) {
-                const int n128 = (Np - ke * NB) / G_BM;
-                syrk_outer_kernel<<<dim3(n128 * (n128 + 1) / 2, nmat), G_THREADS, GEMM128_SMEM, st>>>(W, d_ids, Np, k0 * NB);
+                // lazy trailing update (see syrk_outer_kernel): panel index pidx = k0 / 4
+                static const bool eager = getenv("GPRN_EAGER_SYRK") != nullptr;
+                const int pidx = k0 / 4, t0 = ke * NB, n128 = (Np - t0) / G_BM;
+                if (eager) {
+                    syrk_outer_kernel<<<dim3(n128 * (n128 + 1) / 2, nmat), G_THREADS, GEMM128_SMEM, st>>>(W, d_ids, Np, k0 * NB, OUTER_KB, t0, 0);
+                } else if (pidx % 2 == 0) {
+                    syrk_outer_kernel<<<dim3(2 * n128 - 1, nmat), G_THREADS, GEMM128_SMEM, st>>>(W, d_ids, Np, k0 * NB, OUTER_KB, t0, 2);
+                } else {
+                    syrk_outer_kernel<<<dim3(n128 * (n128 + 1) / 2, nmat), G_THREADS, GEMM128_SMEM, st>>>(W, d_ids, Np, (k0 - 4) * NB, 2 * OUTER_KB, t0, 0);
+                }
             } else {
                 const int n = nt - ke;
                 syrk_update_kernel<<<dim3(n * (n + 1) / 2, nmat), 128, 2 * TILE_SMEM, st>>>(W, d_ids, Np, k0, ke);
