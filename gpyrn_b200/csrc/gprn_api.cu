@@ -145,6 +145,7 @@ static int set_kernel_attrs() {
     CU(cudaFuncSetAttribute(small_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM));
     CU(cudaFuncSetAttribute(cross_frob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(predict_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
+    CU(cudaFuncSetAttribute(predict_norm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM128_SMEM));
     g_attr_done = true;
     return 0;
 }
@@ -877,16 +878,19 @@ extern "C" int gprn_predict(gprn_handle* h, const double* hyper, const double* m
     if (solve_batch(h, ck.X, ck.d_ids_all, M, c.vv, c.zv, c.uv, c.gv, ck.vec_elems, st)) return 1;   // uv = alpha
     // test points in chunks
     const int TC = 4096;
-    const int Tc = std::min(TC, ((T + NB - 1) / NB) * NB);
+    const bool big = (Np % G_BN == 0) && Np >= 256;          // 128x128 GEMM core for the variance norms
+    const int tunit = big ? G_BM : NB;
+    const int Tc = std::min(TC, ((T + tunit - 1) / tunit) * tunit);
+    const int nparts = big ? Np / G_BN : 1;
     // ks: Kstar chunk [Tc][Np]; pred: tstar[T], gp_mean[M][T], gp_var[M][T], rownorm[Tc], mean_t[p][T], out mean/var [T*p]x2
     if (ensure(h->ks, sizeof(double) * (size_t)Tc * Np)) return 1;
-    const size_t pd = (size_t)T + 2 * (size_t)M * T + Tc + (size_t)p * T + 2 * (size_t)T * p;
+    const size_t pd = (size_t)T + 2 * (size_t)M * T + (size_t)nparts * Tc + (size_t)p * T + 2 * (size_t)T * p;
     if (ensure(h->pred, sizeof(double) * pd)) return 1;
     double* d_ts = (double*)h->pred.p;
     double* d_gm = d_ts + T;
     double* d_gv = d_gm + (size_t)M * T;
     double* d_rn = d_gv + (size_t)M * T;
-    double* d_mt = d_rn + Tc;
+    double* d_mt = d_rn + (size_t)nparts * Tc;
     double* d_pm = d_mt + (size_t)p * T;
     double* d_pv = d_pm + (size_t)T * p;
     double* d_ks = (double*)h->ks.p;
@@ -901,7 +905,7 @@ extern "C" int gprn_predict(gprn_handle* h, const double* hyper, const double* m
         const int32_t* tok = h->d_tok + (size_t)m * GPRN_MAX_PROG;
         for (int t0 = 0; t0 < T; t0 += Tc) {
             const int tn = std::min(Tc, T - t0);
-            const int tpad = ((tn + NB - 1) / NB) * NB;
+            const int tpad = ((tn + tunit - 1) / tunit) * tunit;
             CU(cudaMemsetAsync(d_ks, 0, sizeof(double) * (size_t)tpad * Np, st));
             // note: with square (T == N) the diagonal-by-position test needs global row indices, so the
             // chunked call is only exact when the whole of tstar fits one chunk; enforce that.
@@ -911,9 +915,12 @@ extern "C" int gprn_predict(gprn_handle* h, const double* hyper, const double* m
             LAUNCH_CHECK(h);
             rect_gemv_kernel<<<(tn + 7) / 8, 256, 0, st>>>(d_gm + (size_t)m * T + t0, d_ks, (size_t)Np, alpha, tn, N);
             LAUNCH_CHECK(h);
-            predict_norm_kernel<<<tpad / NB, 128, 2 * TILE_SMEM, st>>>(d_rn, d_ks, Xm, Np, N);
+            if (big)
+                predict_norm128_kernel<<<dim3(tpad / G_BM, Np / G_BN), G_THREADS, GEMM128_SMEM, st>>>(d_rn, Tc, d_ks, Xm, Np);
+            else
+                predict_norm_kernel<<<tpad / NB, 128, 2 * TILE_SMEM, st>>>(d_rn, d_ks, Xm, Np, N);
             LAUNCH_CHECK(h);
-            predict_var_kernel<<<(tn + 255) / 256, 256, 0, st>>>(d_gv + (size_t)m * T + t0, d_rn, tn, tok, h->h_len[m], par, 1.25e-12);
+            predict_var_kernel<<<(tn + 255) / 256, 256, 0, st>>>(d_gv + (size_t)m * T + t0, d_rn, nparts, Tc, tn, tok, h->h_len[m], par, 1.25e-12);
             LAUNCH_CHECK(h);
         }
     }

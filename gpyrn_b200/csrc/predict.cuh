@@ -10,6 +10,7 @@
 #pragma once
 #include "common.cuh"
 #include "assemble.cuh"
+#include "gemm128.cuh"
 
 namespace gprn {
 
@@ -74,14 +75,56 @@ __global__ void __launch_bounds__(128) predict_norm_kernel(double* __restrict__ 
     if (tid < NB) rownorm2[blockIdx.x * NB + tid] = rs[0][tid] + rs[1][tid];
 }
 
+// Large-N variant of predict_norm_kernel on the 128x128 DMMA GEMM core: CTA (tt, at) forms the tile
+// C[t][a] = sum_{n <= a} Ks[t][n] X[a][n] for 128 test epochs x 128 rows of X (K = a0 + 128, X lower triangular),
+// squares it and writes the 128 row sums to partial[at][t]; predict_var_kernel adds the partials in tile order.
+// Ks: [Tpad][Np] with zero padding (columns >= N, rows >= T).  grid = (Tpad/128, Np/128), block = G_THREADS,
+// dynamic smem GEMM128_SMEM.  blockIdx.y is mapped to descending a so that the long-K tiles start first.
+__global__ void __launch_bounds__(G_THREADS) predict_norm128_kernel(double* __restrict__ partial, int Tpad,
+                                                                    const double* __restrict__ Ks,
+                                                                    const double* __restrict__ X, int Np) {
+    extern __shared__ double smem[];
+    __shared__ double rs[G_WARPS_N][G_BM];
+    const int na = Np / G_BN;
+    const int at = na - 1 - blockIdx.y, a0 = at * G_BN, t0 = blockIdx.x * G_BM;
+    double acc[G_MI][4][2];
+#pragma unroll
+    for (int i = 0; i < G_MI; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    gemm128_mainloop<false>(acc, smem, Ks + (size_t)t0 * Np, Np, X + (size_t)a0 * Np, Np, a0 + G_BN);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3;
+    const int r = lane >> 2, c = lane & 3;
+#pragma unroll
+    for (int i = 0; i < G_MI; i++) {
+        double sr = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            sr = fma(acc[i][j][0], acc[i][j][0], sr);
+            sr = fma(acc[i][j][1], acc[i][j][1], sr);
+        }
+        sr += __shfl_xor_sync(0xffffffffu, sr, 1);
+        sr += __shfl_xor_sync(0xffffffffu, sr, 2);
+        if (c == 0) rs[wn][wm * G_WM + i * 8 + r] = sr;
+    }
+    __syncthreads();
+    if (threadIdx.x < G_BM) {
+        const int t = threadIdx.x;
+        partial[(size_t)at * Tpad + t0 + t] = (rs[0][t] + rs[1][t]) + (rs[2][t] + rs[3][t]);
+    }
+}
+
 // var[t] = k(0) + nugget - rownorm2[t]   (diagonal of Kstarstar, _gp.py:131,136-137)
-__global__ void predict_var_kernel(double* __restrict__ var, const double* __restrict__ rownorm2, int T,
-                                   const int32_t* __restrict__ tok, int ntok, const double* __restrict__ par,
-                                   double nugget) {
+// rownorm2: [nparts][stride] partial sums (nparts = 1 for predict_norm_kernel), added in order.
+__global__ void predict_var_kernel(double* __restrict__ var, const double* __restrict__ rownorm2, int nparts,
+                                   int stride, int T, const int32_t* __restrict__ tok, int ntok,
+                                   const double* __restrict__ par, double nugget) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     double k0 = eval_prog(tok, ntok, par, 0.0, true, false) + nugget;
-    var[t] = k0 - rownorm2[t];
+    double s = 0.0;
+    for (int a = 0; a < nparts; a++) s += rownorm2[(size_t)a * stride + t];
+    var[t] = k0 - s;
 }
 
 // GPRN combination (meanfield.py:1364-1372; jitter^2 added once per node, quirk Q6).

@@ -18,6 +18,7 @@ t0 = time.time(); elbo, mu, var, it = g.ELBOcalc(max_iter=6); print(f"ELBOcalc(m
 span = m.time[-1] - m.time[0]
 tstar = np.linspace(m.time[0] - 0.2 * span, m.time[-1] + 0.2 * span, T)
 g._Prediction(tstar=tstar[:256], mu=mu, var=var)
+g._Prediction(tstar=tstar, mu=mu, var=var)
 t0 = time.time(); pm, pv = g._Prediction(tstar=tstar, mu=mu, var=var); dt = time.time() - t0
 M = q * (p + 1)
 print(f"_Prediction T={T}: {dt:.3f} s  ({M * (N**3/3 + N**2*T) / dt * 1e-12:.2f} TFLOP/s algorithmic, SURVEY 8d F_pred)")
