@@ -66,9 +66,9 @@ struct gprn_handle {
     bool model_set = false;
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    static const int NAUX = 4;
-    cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr, nullptr, nullptr};
+    static const int NAUX = 8;
+    cudaStream_t aux[NAUX] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
     int64_t launches = 0;
     double last_ms = 0.0;
     int64_t last_total_iters = 0;
@@ -387,7 +387,7 @@ static int factor_batch(gprn_handle* h, double* W, const int* d_ids, int nmat, d
 static int factor_batch_multi(gprn_handle* h, double* W, const int* d_ids, int nmat, double* logdet, int* mstatus,
                               int* ctr, double* X, cudaStream_t st) {
     static const int groups_env = getenv("GPRN_FACTOR_GROUPS") ? atoi(getenv("GPRN_FACTOR_GROUPS")) : 0;
-    int G = groups_env > 0 ? groups_env : gprn_handle::NAUX;
+    int G = groups_env > 0 ? groups_env : 4;
     if (!use_two_level(h->Np) || nmat < 2 || G < 2) return factor_batch(h, W, d_ids, nmat, logdet, mstatus, ctr, X, st);
     G = std::min(std::min(G, (int)gprn_handle::NAUX), nmat);
     CU(cudaEventRecord(h->ev_fork, st));
