@@ -128,7 +128,11 @@ __device__ __forceinline__ void potrf64(const double* Td, int ldd, double* Ls, d
     double a[16];
 #pragma unroll
     for (int u = 0; u < 16; u++) a[u] = Td[r * ldd + q4 + 4 * u];
-    if (q4 == 0) col[r] = a[0];
+    __syncthreads();                       // Td fully read: Ls (which may alias it) can be written from here on
+    // Finished (unscaled) columns are parked in Ls the moment they are published, so the update below needs no
+    // "column already final" / "above the diagonal" predicates: registers of dead elements may hold garbage, it is
+    // never read.  This halves the instructions of a pivot step (the step is issue- as much as latency-bound).
+    if (q4 == 0) { col[r] = a[0]; Ls[r * LDT] = a[0]; }
     __syncthreads();
 #pragma unroll
     for (int c = 0; c < NB; c++) {
@@ -141,13 +145,14 @@ __device__ __forceinline__ void potrf64(const double* Td, int ldd, double* Ls, d
         if (r > c) {
             const double t = cb[r] * (1.0 / piv);
 #pragma unroll
-            for (int u = c >> 2; u < 16; u++) {
-                const int cc = q4 + 4 * u;
-                if (cc > c && cc <= r) a[u] = fma(-t, cb[cc], a[u]);
-            }
+            for (int u = c >> 2; u < 16; u++) a[u] = fma(-t, cb[q4 + 4 * u], a[u]);
         }
         if (c + 1 < NB) {
-            if (q4 == ((c + 1) & 3)) col[((c + 1) & 1) * NB + r] = a[(c + 1) >> 2];
+            if (q4 == ((c + 1) & 3)) {
+                const double v = a[(c + 1) >> 2];
+                col[((c + 1) & 1) * NB + r] = v;
+                Ls[r * LDT + c + 1] = v;
+            }
             __syncthreads();
         }
     }
@@ -158,7 +163,7 @@ __device__ __forceinline__ void potrf64(const double* Td, int ldd, double* Ls, d
     for (int u = 0; u < 16; u++) {
         const int cc = q4 + 4 * u;
         double v = 0.0;
-        if (cc < r) v = a[u] * rd[cc];
+        if (cc < r) v = Ls[r * LDT + cc] * rd[cc];
         else if (cc == r) v = sqrt(pivs[r]);
         Ls[r * LDT + cc] = v;
     }
