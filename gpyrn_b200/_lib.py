@@ -41,6 +41,8 @@ SIGNATURES = {
                                   ctypes.c_int64, ctypes.c_int64, ctypes.c_int, c_double_p]),
     "gprn_predict": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, ctypes.c_int,
                                     c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, ctypes.c_void_p]),
+    "gprn_sample": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_double, c_double_p,
+                                   ctypes.c_void_p]),
     "gprn_debug_factor": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p, c_double_p, c_double_p,
                                          c_double_p]),
     "gprn_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),

@@ -3,8 +3,8 @@
 Same public surface as the reference's ``gpyrn.covfunc`` for the kernels on the hot path
 (``SquaredExponential``, ``Periodic``, ``QuasiPeriodic``, ``RationalQuadratic``, ``Matern32``,
 ``Matern52``, ``WhiteNoise`` and their ``+`` / ``*`` compositions; reference gpyrn/covfunc.py:5-80,
-128-288, 355-396), plus the four cheap "next" kernels of SURVEY.md 8(f).3 (``Constant``, ``RQP``, ``Cosine``,
-``Exponential``; covfunc.py:107-125, 291-352): ``.pars`` float64 array, ``_param_names``, ``_tag``, ``get_parameters`` /
+128-288, 355-396), plus the "next" kernels of SURVEY.md 8(f).3 (``Constant``, ``RQP``, ``Cosine``,
+``Exponential``; covfunc.py:107-125, 291-352; ``Derivative`` of SE / Periodic / QuasiPeriodic, covfunc.py:80-104): ``.pars`` float64 array, ``_param_names``, ``_tag``, ``get_parameters`` /
 ``set_parameters``, ``k(r)`` on an array of lags.
 
 The objects hold parameters and structure only.  All arithmetic happens on the GPU: ``k(r)`` ships
@@ -21,6 +21,7 @@ from . import _lib
 # opcodes of include/gprn_b200.h
 OP_SE, OP_PER, OP_QP, OP_RQ, OP_M32, OP_M52, OP_WN, OP_ADD, OP_MUL = 1, 2, 3, 4, 5, 6, 7, 100, 101
 OP_CONST, OP_RQP, OP_COS, OP_EXP = 8, 9, 10, 11
+OP_DSE, OP_DPER, OP_DQP = 12, 13, 14
 
 
 class covFunction:
@@ -120,6 +121,30 @@ class Multiplication(_operator):
     _symbol, _join = '*', OP_MUL
 
 
+class Derivative(covFunction):
+    r""":math:`\partial^2 k / \partial x_i \partial x_j` of a twice-differentiable kernel (SquaredExponential, Periodic,
+    QuasiPeriodic); shares the parameters of ``k`` (reference covfunc.py:80-104)."""
+
+    def __init__(self, k):
+        if not getattr(k, '_twice_differentiable', False) or getattr(k, '_dopcode', None) is None:
+            raise ValueError(f'kernel {k} is not twice differentiable')
+        self.k = k
+        self.kerneltype = 'complex_unary'
+        self.pars = self.k.pars
+        self._param_names = self.k._param_names
+        self._tag = 'd' + self.k._tag
+
+    def program(self):
+        return [self.k._dopcode]
+
+    def _assign(self, values):
+        self.pars = np.array(values, dtype=float)
+        self.k._assign(self.pars)
+
+    def __repr__(self):
+        return f"d {self.k}"
+
+
 class Constant(covFunction):
     r""":math:`K_{ij} = c^2`"""
     _param_names = 'c',
@@ -176,6 +201,7 @@ class SquaredExponential(covFunction):
     _param_names = 'theta', 'ell'
     _tag = 'SE'
     _opcode = OP_SE
+    _dopcode = OP_DSE
     _twice_differentiable = True
 
     def __init__(self, theta: float, ell: float):
@@ -187,6 +213,7 @@ class Periodic(covFunction):
     _param_names = 'theta', 'P', 'ell'
     _tag = 'P'
     _opcode = OP_PER
+    _dopcode = OP_DPER
     _twice_differentiable = True
 
     def __init__(self, theta: float, P: float, ell: float):
@@ -198,6 +225,7 @@ class QuasiPeriodic(covFunction):
     _param_names = 'theta', 'le', 'P', 'lp'
     _tag = 'QP'
     _opcode = OP_QP
+    _dopcode = OP_DQP
     _twice_differentiable = True
 
     def __init__(self, theta: float, elle: float, P: float, ellp: float):

@@ -91,6 +91,36 @@ __device__ __forceinline__ double eval_prog(const int32_t* __restrict__ tok, int
                 st[sp++] = (th * th) * exp((-ar) / l);
                 pp += 2;
             } break;
+            case GPRN_OP_DSE: {  // covfunc.py:182-185
+                double th = par[pp], l = par[pp + 1];
+                double term1 = (th * th) / pow(l, 4.0);
+                double term2 = l * l - r * r;
+                st[sp++] = (term1 * term2) * exp(((-0.5) * (r * r)) / (l * l));
+                pp += 2;
+            } break;
+            case GPRN_OP_DPER: {  // covfunc.py:215-221
+                double th = par[pp], P = par[pp + 1], l = par[pp + 2];
+                double rP = (M_PI * r) / P;
+                double s = sin(rP), c = cos(rP);
+                double term1 = (4.0 * (M_PI * M_PI)) * (th * th);
+                double term2 = (l * l) * cos(2.0 * rP) - (4.0 * (s * s)) * (c * c);
+                double term3 = exp(((-2.0) * (s * s)) / (l * l));
+                st[sp++] = (term1 * term2) * term3;
+                pp += 3;
+            } break;
+            case GPRN_OP_DQP: {  // covfunc.py:257-266
+                double th = par[pp], le = par[pp + 1], P = par[pp + 2], lp = par[pp + 3];
+                double P2 = P * P, lp2 = lp * lp, le2 = le * le, lp4 = pow(lp, 4.0), le4 = pow(le, 4.0);
+                double term1 = (2.0 * (th * th)) / ((P2 * lp4) * le4);
+                double sp1 = sin((M_PI * r) / P), cp1 = cos((M_PI * r) / P);
+                double term2 = (((P2 * lp4) * le2 - ((2.0 * P2) * lp4) * (r * r)) -
+                                ((((4.0 * M_PI) * P) * lp2) * le2) * r * sin(((2.0 * M_PI) * r) / P)) +
+                               (((2.0 * (M_PI * M_PI)) * lp2) * le4) * cos(((2.0 * M_PI) * r) / P) -
+                               ((((8.0 * (M_PI * M_PI)) * le4) * (sp1 * sp1)) * (cp1 * cp1));
+                double term3 = exp((-(lp2 * (r * r) + (2.0 * le2) * (sp1 * sp1))) / (lp2 * le2));
+                st[sp++] = (term1 * term2) * term3;
+                pp += 4;
+            } break;
             case GPRN_OP_ADD: {
                 sp--;
                 st[sp - 1] = st[sp - 1] + st[sp];

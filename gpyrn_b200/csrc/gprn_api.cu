@@ -249,6 +249,9 @@ static int op_npar(int op) {
         case GPRN_OP_RQP: return 5;
         case GPRN_OP_COS: return 2;
         case GPRN_OP_EXP: return 2;
+        case GPRN_OP_DSE: return 2;
+        case GPRN_OP_DPER: return 3;
+        case GPRN_OP_DQP: return 4;
         case GPRN_OP_ADD: case GPRN_OP_MUL: return 0;
         default: return -1;
     }
@@ -935,6 +938,51 @@ extern "C" int gprn_predict(gprn_handle* h, const double* hyper, const double* m
     CU(cudaStreamSynchronize(st));
     for (int m = 0; m < std::min(M, 64); m++)
         if (mst[m]) return fail("gprn_predict: K + diag(var) is not positive definite for component " + std::to_string(m));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prior draws
+// ------------------------------------------------------------------------------------------------
+extern "C" int gprn_sample(gprn_handle* h, const double* hyper, const double* z, double nugget, double* out,
+                           void* stream) {
+    if (!h || !hyper || !z || !out) return fail("gprn_sample: null argument");
+    if (!h->model_set) return fail("gprn_sample: call gprn_set_model first");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->own_stream;
+    const int N = h->N, Np = h->Np, nt = h->nt, M = h->M;
+    const int ntri = nt * (nt + 1) / 2;
+    Chunk ck;
+    if (setup_chunk(h, 1, ck, false, true)) return 1;
+    ElboCtx& c = ck.c;
+    CU(cudaMemcpyAsync((void*)c.hyper, hyper, sizeof(double) * h->H, cudaMemcpyHostToDevice, st));
+    std::vector<double> zp((size_t)M * Np, 0.0);
+    for (int m = 0; m < M; m++)
+        for (int n = 0; n < N; n++) zp[(size_t)m * Np + n] = z[(size_t)m * N + n];
+    CU(cudaMemcpyAsync(c.vv, zp.data(), sizeof(double) * M * Np, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(c.Dv, 0, sizeof(double) * M * Np, st));
+    std::vector<int> act(1, 0);
+    if (upload_lists(h, ck, act, st)) return 1;
+    ProgTable pt{h->d_tok, h->d_len, h->d_par_off};
+    kassemble_sym_kernel<<<dim3(ntri, M, 1), 256, 0, st>>>(ck.K, h->d_time, c.hyper, h->H, pt, M, N, Np, nugget);
+    LAUNCH_CHECK(h);
+    CU(cudaMemsetAsync(c.logdetA, 0, sizeof(double) * M, st));
+    CU(cudaMemsetAsync(c.mstatus, 0, sizeof(int) * M, st));
+    CU(cudaMemsetAsync(ck.d_ctr, 0, sizeof(int) * M, st));
+    form_a_kernel<<<dim3(ntri, M), 256, 0, st>>>(ck.W, ck.K, c.Dv, ck.d_ids_all, Np);
+    LAUNCH_CHECK(h);
+    if (factor_batch_multi(h, ck.W, ck.d_ids_all, M, c.logdetA, c.mstatus, ck.d_ctr, nullptr, st)) return 1;
+    trmv_lower_kernel<<<dim3(Np / 8, M), 256, 0, st>>>(c.zv, ck.W, c.vv, ck.d_ids_all, nullptr, Np);   // L z
+    LAUNCH_CHECK(h);
+    for (int m = 0; m < M; m++)
+        CU(cudaMemcpyAsync(out + (size_t)m * N, c.zv + (size_t)m * Np, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+    int mst[64];
+    CU(cudaMemcpyAsync(mst, c.mstatus, sizeof(int) * std::min(M, 64), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int m = 0; m < std::min(M, 64); m++)
+        if (mst[m])
+            return fail("gprn_sample: K + nugget*I is not positive definite for component " + std::to_string(m) +
+                        " (raise the nugget or add a WhiteNoise term)");
     return 0;
 }
 

@@ -309,6 +309,42 @@ class inference:
     def _randomMuVar(self):
         return np.random.randn(self.d, 1), np.random.rand(self.d, 1)
 
+    def sample(self, time=None, z=None, nugget=1.25e-12):
+        """
+        Draws from the GP priors of the nodes and weights on ``self.time`` (reference :517-539; like the reference,
+        the ``time`` argument is accepted and ignored).
+
+        Args:
+            z: optional standard-normal variates, array (q + q*p, N), nodes first; default ``np.random.randn``
+            nugget: diagonal term (reference ``_tinyNuggetKMatrix``: 1.25e-12).  The draw is ``chol(K + nugget I) z``
+                on the device; the reference's eigen-decomposition route (``allow_singular=True``) is the same
+                distribution.  A kernel matrix that is not numerically positive definite raises ``GprnError``.
+
+        Returns:
+            node_samples (q, N), weight_samples (q*p, N)
+        """
+        nodes, weights, _, jitters = self._get_components()
+        self._bind_model(nodes, weights)
+        M = self.q + self.qp
+        z = np.random.randn(M, self.N) if z is None else np.asarray(z, dtype=float).reshape(M, self.N)
+        hyper = _lib.f64(self._hyper_vector(nodes, weights, jitters))
+        out = np.empty((M, self.N))
+        _lib.check(_lib.lib().gprn_sample(self._h(), _lib.dptr(hyper), _lib.dptr(_lib.f64(z)), float(nugget),
+                                          _lib.dptr(out), None))
+        return out[:self.q].copy(), out[self.q:].copy()
+
+    def _sample_from_gp(self, kernel, time=None, z=None):
+        """One draw from ``kernel`` on ``time`` (default ``self.time``; reference :517-530)."""
+        time = self.time if time is None else np.atleast_1d(np.asarray(time, dtype=float))
+        g = inference(1, time, np.zeros_like(time), np.ones_like(time), device=self.device)
+        try:
+            g.set_components(kernel, covfunc.WhiteNoise(1.0), meanfunc.Constant(0.0), 0.1)   # weight: K = I, unused
+            nodes, _ = g.sample(z=None if z is None else np.vstack([np.asarray(z, dtype=float).ravel(),
+                                                                    np.zeros(time.size)]))
+        finally:
+            g.close()
+        return nodes[0]
+
     # ------------------------------------------------------------------------------------------
     # ELBO
     # ------------------------------------------------------------------------------------------
@@ -569,6 +605,48 @@ class inference:
             sep = np.empty(2, dtype=object)
             sep[0], sep[1] = npred, wpred
             return pm, pv, sep
+        return pm, pv
+
+    def Prediction_batch(self, parameters, tstar=None, max_iter=None, return_info=False):
+        """
+        Predictive mean / variance for B hyper-parameter sets (a posterior chain): each set's
+        variational state is converged on the device (``ELBO_batch``) and then fed to the predictive
+        (``_Prediction``, reference :1289-1379).  The object's own parameters are left untouched.
+
+        Args:
+            parameters: array (B, n_parameters) or (B, number of free parameters), ``get_parameters`` order
+            tstar: test epochs (default: the training epochs)
+
+        Returns:
+            mean (B, T, p), variance (B, T, p) [, elbo (B,), iterations (B,), status (B,)]
+        """
+        self._require_components()
+        P = np.atleast_2d(np.asarray(parameters, dtype=float))
+        B = P.shape[0]
+        if P.shape[1] != self.n_parameters:
+            full = np.tile(self.get_parameters(include_frozen=True), (B, 1))
+            full[:, ~self.frozen_mask] = P
+            P = full
+        tstar = self.time if tstar is None else np.atleast_1d(np.asarray(tstar, dtype=float))
+        elbo, iters, status, mu, var = self.ELBO_batch(P, max_iter=max_iter, return_info=True, return_state=True)
+        n_kernel = sum(k.pars.size for k in chain(self.nodes, self.weights))
+        n_mean = sum(m.pars.size for m in self.means if isinstance(m, meanfunc.meanFunction))
+        T = tstar.size
+        ts = _lib.f64(tstar)
+        pm, pv = np.empty((B, T, self.p)), np.empty((B, T, self.p))
+        saved = [m.pars.copy() if isinstance(m, meanfunc.meanFunction) else None for m in self.means]
+        try:
+            for b in range(B):
+                self._assign_means(P[b, n_kernel:n_kernel + n_mean])
+                mean_t = _lib.f64(self._mean(self.means, tstar))
+                hyper = _lib.f64(np.concatenate([P[b, :n_kernel], P[b, n_kernel + n_mean:]]))
+                _lib.check(_lib.lib().gprn_predict(self._h(), _lib.dptr(hyper), _lib.dptr(_lib.f64(mu[b])),
+                                                   _lib.dptr(_lib.f64(var[b])), _lib.dptr(ts), T, _lib.dptr(mean_t),
+                                                   _lib.dptr(pm[b]), _lib.dptr(pv[b]), None, None, None))
+        finally:
+            self._restore_means(saved)
+        if return_info:
+            return pm, pv, elbo, iters, status
         return pm, pv
 
     def predict(self, tstar=None, nn=1000):

@@ -42,6 +42,11 @@ enum {
     GPRN_OP_RQP = 9,   /* theta, alpha, elle, P, ellp    */
     GPRN_OP_COS = 10,  /* theta, P                       */
     GPRN_OP_EXP = 11,  /* theta, ell                     */
+    /* Derivative(k) = d2k/dxi dxj of the twice-differentiable kernels (covfunc.py:80-104 Derivative;
+     * :182-185 SE._dkdxidj, :215-221 Periodic._dkdxidj, :257-266 QuasiPeriodic._dkdxidj); same parameters as k */
+    GPRN_OP_DSE = 12,  /* theta, ell                     */
+    GPRN_OP_DPER = 13, /* theta, P, ell                  */
+    GPRN_OP_DQP = 14,  /* theta, elle, P, ellp           */
     GPRN_OP_ADD = 100,
     GPRN_OP_MUL = 101
 };
@@ -118,6 +123,14 @@ int gprn_keval(int device, const int32_t* prog, int prog_len, const double* pars
  * _gp.GP.prediction (gpyrn/_gp.py:107-138).
  *   hyper[n_hyper], mu[d], var[d] host; tstar[T]; mean_at_tstar[p*T] (host-evaluated mean functions)
  *   pred_mean[T*p], pred_var[T*p] row-major (T,p); node_pred[q*T], weight_pred[q*p*T] may be NULL. */
+/* Prior draws of all M component GPs on the training epochs: out[m][:] = chol(K_m + nugget*I) z[m][:], with z
+ * standard-normal variates supplied by the caller (host, M*N; component order j nodes, then q + j*p + i weights).
+ * Replaces inference.sample / _sample_from_gp (gpyrn/meanfield.py:517-539) on K = _tinyNuggetKMatrix
+ * (:436-453, nugget 1.25e-12).  The reference draws through scipy's eigen-decomposition (allow_singular=True);
+ * the Cholesky factor gives the same distribution whenever K + nugget*I is numerically positive definite and
+ * an error (no CPU fallback) when it is not. */
+int gprn_sample(gprn_handle* h, const double* hyper, const double* z, double nugget, double* out, void* stream);
+
 int gprn_predict(gprn_handle* h, const double* hyper, const double* mu, const double* var,
                  const double* tstar, int T, const double* mean_at_tstar, double* pred_mean,
                  double* pred_var, double* node_pred, double* weight_pred, void* stream);

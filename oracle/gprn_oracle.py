@@ -20,6 +20,7 @@ Kernel specification used throughout (a tiny expression tree, no reference class
     ("SE", theta, ell) | ("P", theta, P, ell) | ("QP", theta, elle, P, ellp) |
     ("RQ", theta, alpha, ell) | ("M32", theta, ell) | ("M52", theta, ell) | ("WN", w) |
     ("C", c) | ("RQP", theta, alpha, elle, P, ellp) | ("COS", theta, P) | ("EXP", theta, ell) |
+    ("dSE", theta, ell) | ("dP", theta, P, ell) | ("dQP", theta, elle, P, ellp)   [Derivative(k)] |
     ("sum", spec1, spec2) | ("mul", spec1, spec2)
 """
 from __future__ import annotations
@@ -67,6 +68,26 @@ def kernel_eval(spec, r):
         return a[0] ** 2 * np.cos(2 * np.pi * np.abs(r) / a[1])
     if tag == "EXP":                      # covfunc.py:351-352
         return a[0] ** 2 * np.exp(-np.abs(r) / a[1])
+    if tag == "dSE":                      # covfunc.py:98-100 (Derivative) -> :182-185
+        term1 = a[0] ** 2 / a[1] ** 4
+        term2 = a[1] ** 2 - r ** 2
+        return term1 * term2 * np.exp(-0.5 * r ** 2 / a[1] ** 2)
+    if tag == "dP":                       # covfunc.py:215-221
+        rP = np.pi * r / a[1]
+        term1 = 4 * np.pi ** 2 * a[0] ** 2
+        term2 = a[2] ** 2 * np.cos(2 * rP) - 4 * np.sin(rP) ** 2 * np.cos(rP) ** 2
+        term3 = np.exp(-2 * np.sin(rP) ** 2 / a[2] ** 2)
+        return term1 * term2 * term3
+    if tag == "dQP":                      # covfunc.py:257-266
+        th, le, P, lp = a
+        term1 = 2 * th ** 2 / (P ** 2 * lp ** 4 * le ** 4)
+        term2 = P ** 2 * lp ** 4 * le ** 2 - \
+            2 * P ** 2 * lp ** 4 * r ** 2 - \
+            4 * np.pi * P * lp ** 2 * le ** 2 * r * np.sin(2 * np.pi * r / P) + \
+            2 * np.pi ** 2 * lp ** 2 * le ** 4 * np.cos(2 * np.pi * r / P) - \
+            8 * np.pi ** 2 * le ** 4 * np.sin(np.pi * r / P) ** 2 * np.cos(np.pi * r / P) ** 2
+        term3 = np.exp(-(lp ** 2 * r ** 2 + 2 * le ** 2 * np.sin(np.pi * r / P) ** 2) / (lp ** 2 * le ** 2))
+        return term1 * term2 * term3
     if tag == "WN":                       # covfunc.py:144-148 (quirk Q9: decided by shape, not by r==0)
         if r.ndim == 2 and r.shape[0] == r.shape[1]:
             return a[0] ** 2 * np.eye(r.shape[0])

@@ -64,6 +64,8 @@ def build_kernel(spec):
         return build_kernel(spec[1]) + build_kernel(spec[2])
     if spec[0] == "mul":
         return build_kernel(spec[1]) * build_kernel(spec[2])
+    if spec[0] in ("dSE", "dP", "dQP"):
+        return covfunc.Derivative(KCLS[spec[0][1:]](*spec[1:]))
     return KCLS[spec[0]](*spec[1:])
 
 
@@ -134,7 +136,9 @@ def kernel_vectors():
              ("sum", ("SE", 1.0, 10.0), ("WN", 0.2)), ("mul", ("SE", 1.0, 10.0), ("P", 1.0, 20.0, 0.5)),
              ("sum", ("mul", ("M52", 1.1, 30.0), ("P", 1.0, 12.0, 0.9)), ("RQ", 0.5, 1.5, 40.0)),
              ("C", 0.7), ("RQP", 1.2, 0.8, 33.0, 19.0, 0.9), ("COS", 0.9, 14.0), ("EXP", 1.1, 25.0),
-             ("sum", ("mul", ("EXP", 1.0, 50.0), ("COS", 1.0, 9.0)), ("C", 0.1))]
+             ("sum", ("mul", ("EXP", 1.0, 50.0), ("COS", 1.0, 9.0)), ("C", 0.1)),
+             ("dSE", 12.0, 11.0), ("dP", 0.2, 17.0, 0.8), ("dQP", 4.0, 35.0, 23.0, 0.6),
+             ("sum", ("mul", ("dSE", 9.0, 10.0), ("M52", 1.0, 30.0)), ("WN", 0.1))]
     out = dict(t=t, tstar=ts, specs=np.array([repr(s) for s in specs]))
     for i, s in enumerate(specs):
         k = build_kernel(s)
@@ -173,12 +177,25 @@ def big_anchors():
         print(f"{name}: ELBO={elbo!r} iters={it}", flush=True)
 
 
+def derivative_case():
+    """Derivative kernels (covfunc.py:80-104) through the whole ELBO / prediction path."""
+    t, ys, es = synth_data(60, 2, seed=11)
+    run_case("deriv_kernels_60_2_1", t, ys, es, [("dQP", 4.0, 60.0, 25.0, 0.9)],
+             [("sum", ("dSE", 30.0, 40.0), ("WN", 0.05)), ("SE", 1.1, 80.0)],
+             [0.0, 0.1], [0.1, 0.1], tstar=np.linspace(t[0], t[-1], 29))
+
+
 def main():
     if "--big" in sys.argv:
         os.makedirs(os.path.join(HERE, "big"), exist_ok=True)
         big_anchors()
         return
     kernel_vectors()
+    if "--kernels" in sys.argv:
+        return
+    derivative_case()
+    if "--deriv" in sys.argv:
+        return
     # notebook data (docs/examples/one_dataset.ipynb; SURVEY.md 8c anchor -267.06958539495247, 4 it)
     from scipy.stats import norm
     np.random.seed(43)

@@ -29,6 +29,8 @@ def build_kernel(spec):
         return build_kernel(spec[1]) + build_kernel(spec[2])
     if spec[0] == "mul":
         return build_kernel(spec[1]) * build_kernel(spec[2])
+    if spec[0] in ("dSE", "dP", "dQP"):
+        return covfunc.Derivative(KCLS[spec[0][1:]](*spec[1:]))
     return KCLS[spec[0]](*spec[1:])
 
 
@@ -343,3 +345,59 @@ def test_workspace_chunking_is_transparent():
     _lib.check(_lib.lib().gprn_set_workspace_limit(g._h(), 7 * 3 * 3 * 128 * 128 * 8 + (1 << 20)))   # ~7 sets per chunk
     got = g.ELBO_batch(P)
     assert np.array_equal(ref, got)
+
+
+# ---------------------------------------------------------------------------------------------
+# rows (f.2), (f.3): prediction over a chain of hyper sets, prior draws, Derivative kernels
+# ---------------------------------------------------------------------------------------------
+def test_prediction_batch_matches_oracle_per_set():
+    """_Prediction over B hyper sets (meanfield.py:1289-1379 applied to a chain): each set equals the oracle run
+    on that set alone -- converged state, then predictive mean / variance to 1e-8."""
+    m = orc.synth(64, 2, 1, seed=8, node="QP")
+    B = 4
+    theta = orc.perturbed_hyper_sets(m, B, 31)
+    g = from_oracle_model(m)
+    before = g.get_parameters().copy()
+    tstar = np.linspace(m.time[0] - 3, m.time[-1] + 5, 37)
+    pm, pv, elbo, iters, status = g.Prediction_batch(full_parameters(m, theta), tstar=tstar, return_info=True)
+    assert pm.shape == pv.shape == (B, 37, m.p)
+    assert np.array_equal(g.get_parameters(), before)
+    for b in range(B):
+        mb = orc.model_with_hyper(m, theta[b])
+        e, mu, var, it = orc.elbo_calc(mb)
+        assert iters[b] == it and abs(elbo[b] - e) <= 1e-10 * abs(e)
+        om, ov, _, _ = orc.prediction(mb, tstar, mu, var, np.repeat(m.mean_vals[:, :1], 37, axis=1))
+        assert rel(pm[b], om) < 1e-8 and rel(pv[b], ov) < 1e-8
+
+
+@pytest.mark.parametrize("N", [50, 300])
+def test_prior_draws_are_cholesky_times_z(N):
+    """sample() (meanfield.py:517-539): draws are chol(K + nugget I) z; checked against numpy's factor of the
+    oracle's kernel matrices for the same z, and for the right covariance through unit vectors."""
+    m = orc.synth(N, 2, 1, seed=12, node="QP")
+    m.nodes = [("sum", m.nodes[0], ("WN", 0.05))]
+    m.weights = [("sum", w, ("WN", 0.05)) for w in m.weights]
+    g = from_oracle_model(m)
+    z = np.random.default_rng(5).standard_normal((3, N))
+    ns, ws = g.sample(z=z)
+    assert ns.shape == (1, N) and ws.shape == (2, N)
+    for k, (spec, got) in enumerate(zip(m.nodes + m.weights, np.vstack([ns, ws]))):
+        L = np.linalg.cholesky(orc.kmatrix(spec, m.time, nugget=1.25e-12))
+        assert rel(got, L @ z[k]) < 1e-10
+    e3 = np.zeros((3, N)); e3[:, 3] = 1.0
+    ns, _ = g.sample(z=e3)                 # column 3 of L
+    K = orc.kmatrix(m.nodes[0], m.time, nugget=1.25e-12)
+    assert rel(ns[0], np.linalg.cholesky(K)[:, 3]) < 1e-10
+    one = g._sample_from_gp(covfunc.SquaredExponential(1.0, 5.0) + covfunc.WhiteNoise(0.1), z=z[0])
+    Lse = np.linalg.cholesky(orc.kmatrix(("sum", ("SE", 1.0, 5.0), ("WN", 0.1)), m.time, nugget=1.25e-12))
+    assert rel(one, Lse @ z[0]) < 1e-10
+    np.random.seed(0)
+    a, b = g.sample()                      # default: numpy's global generator
+    assert np.all(np.isfinite(a)) and np.all(np.isfinite(b))
+
+
+def test_prior_draw_of_singular_kernel_raises():
+    m = orc.synth(200, 1, 1, seed=2, node="QP")
+    g = inference_from(m.time, m.y, m.yerr, [("SE", 1.0, 500.0)], m.weights, [0.0], m.jitters)
+    with pytest.raises(_lib.GprnError):
+        g.sample(nugget=-2.0)              # first pivot 1 - 2 < 0: deterministic "not positive definite"

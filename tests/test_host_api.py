@@ -121,6 +121,24 @@ def test_kernel_programs_and_composition():
         covfunc.SquaredExponential(1, 2).set_parameters([3])
 
 
+def test_Derivative_kernel_objects():
+    """reference covfunc.py:80-104: only twice-differentiable kernels, tag 'd'+tag, parameters shared with k."""
+    qp = covfunc.QuasiPeriodic(1, 2, 3, 4)
+    d = covfunc.Derivative(qp)
+    assert d._tag == 'dQP' and d._param_names == qp._param_names and d.kerneltype == 'complex_unary'
+    assert d.program() == [covfunc.OP_DQP] and np.allclose(d.pars, [1, 2, 3, 4])
+    assert covfunc.Derivative(covfunc.SquaredExponential(1, 2)).program() == [covfunc.OP_DSE]
+    assert covfunc.Derivative(covfunc.Periodic(1, 2, 3)).program() == [covfunc.OP_DPER]
+    k = d * covfunc.Matern52(1, 5)
+    assert k.program() == [covfunc.OP_DQP, covfunc.OP_M52, covfunc.OP_MUL]
+    k.set_parameters([5, 6, 7, 8, 9, 10])
+    assert np.allclose(qp.pars, [5, 6, 7, 8])
+    with pytest.raises(ValueError):
+        covfunc.Derivative(covfunc.Matern52(1, 2))
+    with pytest.raises(ValueError):
+        covfunc.Derivative(covfunc.Periodic(1, 2, 3) + covfunc.WhiteNoise(1))
+
+
 def test_Constant():
     m = Constant(0.0)
     assert m.pars[0] == 0.0 and np.all(m(np.random.rand(10)) == 0.0)

@@ -33,6 +33,8 @@ def build_kernel(spec):
         return build_kernel(spec[1]) + build_kernel(spec[2])
     if spec[0] == "mul":
         return build_kernel(spec[1]) * build_kernel(spec[2])
+    if spec[0] in ("dSE", "dP", "dQP"):
+        return covfunc.Derivative(KCLS[spec[0][1:]](*spec[1:]))
     return KCLS[spec[0]](*spec[1:])
 
 
