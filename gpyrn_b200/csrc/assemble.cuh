@@ -141,6 +141,7 @@ __device__ __forceinline__ double eval_prog(const int32_t* __restrict__ tok, int
 __global__ void __launch_bounds__(256) kassemble_sym_kernel(double* __restrict__ K, const double* __restrict__ time,
                                                             const double* __restrict__ hyper, int H, ProgTable pt,
                                                             int M, int N, int Np, double nugget) {
+    GPRN_TRACE_SCOPE(TK_KASSEMBLE);
     __shared__ double ti[NB], tj[NB];
     __shared__ int32_t stok[GPRN_MAX_PROG];
     __shared__ double spar[GPRN_MAX_PROG * 4];

@@ -170,6 +170,39 @@ __device__ __forceinline__ void potrf64(const double* Td, int ldd, double* Ls, d
     __syncthreads();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Per-CTA execution trace (development aid, compiled in only with -DGPRN_TRACE; see tools/trace_run.py):
+// every CTA of the traced kernels appends (kernel id, SM id, start, end in globaltimer ns) to a device buffer.
+// ------------------------------------------------------------------------------------------------
+#ifdef GPRN_TRACE
+struct TraceRec { unsigned long long t0, t1; int kid, smid; };
+__device__ TraceRec* g_trace_buf = nullptr;
+__device__ unsigned int g_trace_n = 0, g_trace_cap = 0;
+struct TraceScope {
+    unsigned long long t0;
+    int kid;
+    __device__ __forceinline__ TraceScope(int k) : t0(0), kid(k) {
+        if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    }
+    __device__ __forceinline__ ~TraceScope() {
+        if (threadIdx.x == 0 && g_trace_buf) {
+            unsigned long long t1;
+            unsigned smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            unsigned i = atomicAdd(&g_trace_n, 1u);
+            if (i < g_trace_cap) g_trace_buf[i] = TraceRec{t0, t1, kid, (int)smid};
+        }
+    }
+};
+#define GPRN_TRACE_SCOPE(k) TraceScope trace_scope_(k)
+#else
+#define GPRN_TRACE_SCOPE(k)
+#endif
+enum { TK_PANEL = 1, TK_POTRF = 2, TK_TRSM = 3, TK_SYRK64 = 4, TK_SYRK_OUTER = 5, TK_TRTRI_DIAG = 6, TK_TRTRI_ROW = 7,
+       TK_TRTRI_OUTER = 8, TK_TRTRI_INBLOCK = 9, TK_TRMV_LOWER = 10, TK_TRMV_UPPER = 11, TK_CROSS_FROB = 12,
+       TK_FORM_A = 13, TK_KASSEMBLE = 14, TK_SMALL = 15, TK_OTHER = 16 };
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -83,6 +83,7 @@ __global__ void init_state_kernel(ElboCtx c) {
 
 // Node right-hand sides (meanfield.py:765, 788-791).  grid = (q, nactive), block = 256.
 __global__ void prep_nodes_kernel(ElboCtx c, const int* __restrict__ sets) {
+    GPRN_TRACE_SCOPE(TK_OTHER);
     const int set = sets[blockIdx.y], j = blockIdx.x;
     const int N = c.N, q = c.q, p = c.p;
     const double* mu = c.mu + (size_t)set * c.d;
@@ -114,6 +115,7 @@ __global__ void prep_nodes_kernel(ElboCtx c, const int* __restrict__ sets) {
 
 // Weight right-hand sides (meanfield.py:838, 847-850, 864).  grid = (q*p, nactive), block = 256.
 __global__ void prep_weights_kernel(ElboCtx c, const int* __restrict__ sets) {
+    GPRN_TRACE_SCOPE(TK_OTHER);
     const int set = sets[blockIdx.y], ji = blockIdx.x, j = ji / c.p, i = ji % c.p;
     const int N = c.N, q = c.q;
     const double* muFn = c.mu_new + (size_t)set * c.d;
@@ -145,6 +147,7 @@ __global__ void prep_weights_kernel(ElboCtx c, const int* __restrict__ sets) {
 // forms are added by quad_kernel.  grid = (nmat_per_set, nactive), block = 256; first = first matrix index
 // of the phase (0 for nodes, q for weights).
 __global__ void post_kernel(ElboCtx c, const int* __restrict__ sets, int first, int use_identity) {
+    GPRN_TRACE_SCOPE(TK_OTHER);
     __shared__ double red[33];
     const int set = sets[blockIdx.y], m = first + blockIdx.x;
     const int N = c.N, q = c.q, p = c.p;
@@ -179,6 +182,7 @@ __global__ void post_kernel(ElboCtx c, const int* __restrict__ sets, int first, 
 // -0.5 * ||z||^2 added to the log-prior accumulator (z = X_K m computed by trmv_lower).
 // grid = (nmat_per_set, nactive), block = 256.
 __global__ void quad_kernel(ElboCtx c, const int* __restrict__ sets, int first) {
+    GPRN_TRACE_SCOPE(TK_OTHER);
     __shared__ double red[33];
     const int set = sets[blockIdx.y], m = first + blockIdx.x;
     const size_t vo = ((size_t)set * c.M + m) * c.Np;
@@ -200,6 +204,7 @@ __global__ void gather_quad_vec_kernel(ElboCtx c, const int* __restrict__ sets, 
 // Cross-node trace, linear part (quirk Q3): -0.5 * sum_{k<j} sum_n D_k[n] * diag(K_j^-1)[n].
 // grid = (nactive), block = 256.
 __global__ void cross_linear_kernel(ElboCtx c, const int* __restrict__ sets) {
+    GPRN_TRACE_SCOPE(TK_OTHER);
     __shared__ double red[33];
     const int set = sets[blockIdx.x];
     double s = 0.0;
@@ -219,6 +224,7 @@ __global__ void cross_linear_kernel(ElboCtx c, const int* __restrict__ sets) {
 __global__ void __launch_bounds__(128) cross_frob_kernel(ElboCtx c, const double* __restrict__ XK,
                                                          const double* __restrict__ XA,
                                                          const int* __restrict__ sets) {
+    GPRN_TRACE_SCOPE(TK_CROSS_FROB);
     extern __shared__ double smem[];
     double* As = smem;
     double* Bs = smem + NB * LDT;
@@ -266,6 +272,7 @@ __global__ void __launch_bounds__(128) cross_frob_kernel(ElboCtx c, const double
 
 // Likelihood term, ELBO assembly, stopping rule, state commit.  grid = (nactive), block = 256.
 __global__ void elbo_finish_kernel(ElboCtx c, const int* __restrict__ sets) {
+    GPRN_TRACE_SCOPE(TK_OTHER);
     __shared__ double red[33];
     const int set = sets[blockIdx.x];
     const int N = c.N, q = c.q, p = c.p;

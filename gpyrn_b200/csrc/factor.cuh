@@ -20,6 +20,7 @@ namespace gprn {
 __global__ void __launch_bounds__(256) form_a_kernel(double* __restrict__ W, const double* __restrict__ K,
                                                      const double* __restrict__ dvec, const int* __restrict__ ids,
                                                      int Np) {
+    GPRN_TRACE_SCOPE(TK_FORM_A);
     int I, J;
     tri_decode(blockIdx.x, I, J);
     const int id = ids[blockIdx.y];
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(256) form_a_kernel(double* __restrict__ W, con
 __global__ void __launch_bounds__(256) panel_col_kernel(double* __restrict__ W, const int* __restrict__ ids, int Np,
                                                         int k, int k0, double* __restrict__ logdet,
                                                         int* __restrict__ status, int* __restrict__ ctr) {
+    GPRN_TRACE_SCOPE(TK_PANEL);
     extern __shared__ double smem[];
     double* Bs = smem;                 // L_kk' operand; then potrf input (stride LDV) and output L_kk (stride LDT)
     double* As0 = smem + NB * LDT;     // L_i0k' / L_i1k' operands; then V (substitution vectors, stride 129)
@@ -140,10 +142,165 @@ __global__ void __launch_bounds__(256) panel_col_kernel(double* __restrict__ W, 
     }
 }
 
+// The same panel step as two launches (default): potrf_col_kernel factors the diagonal tile once per matrix,
+// trsm_col_kernel then solves FOUR row tiles per CTA (all 256 threads carry a substitution vector).  Compared with
+// panel_col_kernel this drops the redundant per-CTA potrf64 and halves the CTA count, so a panel step holds
+// roughly a third of the SM time -- SMs that the 128x128 GEMM launches of the other stream groups can use
+// (a GEMM CTA needs a whole register file, so it never shares an SM with a panel CTA).  Same arithmetic, same
+// summation order as panel_col_kernel: the factors are bit-identical.
+// potrf_col_kernel: grid = (nmat), block = 256, dynamic smem POTRF_COL_SMEM.
+#define POTRF_COL_SMEM ((NB * LDT + 4 * NB) * sizeof(double))
+__global__ void __launch_bounds__(256) potrf_col_kernel(double* __restrict__ W, const int* __restrict__ ids, int Np,
+                                                        int k, int k0, double* __restrict__ logdet,
+                                                        int* __restrict__ status) {
+    GPRN_TRACE_SCOPE(TK_POTRF);
+    extern __shared__ double smem[];
+    double* Bs = smem;                 // L_kk' operand; then potrf input (stride LDV) and output L_kk (stride LDT)
+    double* col = smem + NB * LDT;
+    double* pivs = col + 2 * NB;
+    double* rd = pivs + NB;
+    __shared__ int bad;
+    const int id = ids[blockIdx.x];
+    double* Wm = W + (size_t)id * Np * Np;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = warp >> 2, w4 = warp & 3, wm = w4 >> 1, wn = w4 & 1;
+    const int r = lane >> 2, c = lane & 3;
+    if (tid == 0) bad = 0;
+    double accd[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int m = wm * 32 + a * 8 + r, n = wn * 32 + b * 8 + 2 * c;
+            accd[a][b][0] = accd[a][b][1] = 0.0;
+            if (grp == 0) {
+                double2 v = *reinterpret_cast<const double2*>(Wm + (size_t)(k * NB + m) * Np + k * NB + n);
+                accd[a][b][0] = v.x; accd[a][b][1] = v.y;
+            }
+        }
+    for (int kp = k0; kp < k; kp++) {
+        load_tile<false>(Bs, Wm + (size_t)(k * NB) * Np + kp * NB, Np, tid, 256);
+        __syncthreads();
+        if (grp == 0) mma_tile<true>(accd, Bs, Bs, wm, wn, lane);
+        __syncthreads();
+    }
+    if (grp == 0) {
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int m = wm * 32 + a * 8 + r, n = wn * 32 + b * 8 + 2 * c;
+                Bs[m * LDV + n] = accd[a][b][0];
+                Bs[m * LDV + n + 1] = accd[a][b][1];
+            }
+    }
+    __syncthreads();
+    potrf64(Bs, LDV, Bs, rd, col, pivs, &bad);
+    double* dst = Wm + (size_t)(k * NB) * Np + k * NB;
+    for (int e = tid; e < NB * NB; e += 256) {
+        int m = e >> 6, n = e & 63;
+        dst[(size_t)m * Np + n] = Bs[m * LDT + n];
+    }
+    if (tid < 32) {
+        double sl = log(pivs[tid]) + log(pivs[tid + 32]);
+        sl = warp_sum(sl);
+        if (tid == 0) {
+            logdet[id] += sl;          // one CTA per matrix and launch, launches of a matrix are stream ordered
+            if (bad) status[id] = 1;
+        }
+    }
+}
+
+// trsm_col_kernel: L_ik = (A_ik - sum_{k'} L_ik' L_kk'^T) L_kk^-T for the row tiles i = k+1+4*blockIdx.x .. +3.
+// Warps 0-3 own the first two tiles, warps 4-7 the other two (one accumulator set each).
+// grid = (ceil((nt-k-1)/4), nmat), block = 256, dynamic smem TRSM_COL_SMEM.
+#define TRSM4_LDV 257
+#define TRSM_COL_SMEM ((5 * NB * LDT + NB) * sizeof(double))
+__global__ void __launch_bounds__(256) trsm_col_kernel(double* __restrict__ W, const int* __restrict__ ids, int Np,
+                                                       int k, int k0) {
+    GPRN_TRACE_SCOPE(TK_TRSM);
+    extern __shared__ double smem[];
+    double* Bs = smem;                 // L_kk' operand, then L_kk
+    double* As = smem + NB * LDT;      // four row-tile operands; then V (substitution vectors, stride 257)
+    double* V = As;
+    double* rd = smem + 5 * NB * LDT;
+    const int nt = Np / NB;
+    const int id = ids[blockIdx.y];
+    double* Wm = W + (size_t)id * Np * Np;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = warp >> 2, w4 = warp & 3, wm = w4 >> 1, wn = w4 & 1, tid4 = tid & 127;
+    const int r = lane >> 2, c = lane & 3;
+    const int ibase = k + 1 + 4 * blockIdx.x;
+    const int ia = ibase + 2 * grp, ib = ia + 1;
+    const bool hasa = ia < nt, hasb = ib < nt;
+    double acca[4][4][2], accb[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int m = wm * 32 + a * 8 + r, n = wn * 32 + b * 8 + 2 * c;
+            acca[a][b][0] = acca[a][b][1] = accb[a][b][0] = accb[a][b][1] = 0.0;
+            if (hasa) {
+                double2 v = *reinterpret_cast<const double2*>(Wm + (size_t)(ia * NB + m) * Np + k * NB + n);
+                acca[a][b][0] = v.x; acca[a][b][1] = v.y;
+            }
+            if (hasb) {
+                double2 v = *reinterpret_cast<const double2*>(Wm + (size_t)(ib * NB + m) * Np + k * NB + n);
+                accb[a][b][0] = v.x; accb[a][b][1] = v.y;
+            }
+        }
+    double* Aa = As + (2 * grp) * NB * LDT;
+    double* Ab = Aa + NB * LDT;
+    for (int kp = k0; kp < k; kp++) {
+        load_tile<false>(Bs, Wm + (size_t)(k * NB) * Np + kp * NB, Np, tid, 256);
+        if (hasa) load_tile<false>(Aa, Wm + (size_t)(ia * NB) * Np + kp * NB, Np, tid4, 128);
+        if (hasb) load_tile<false>(Ab, Wm + (size_t)(ib * NB) * Np + kp * NB, Np, tid4, 128);
+        __syncthreads();
+        if (hasa) mma_tile<true>(acca, Aa, Bs, wm, wn, lane);
+        if (hasb) mma_tile<true>(accb, Ab, Bs, wm, wn, lane);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int m = wm * 32 + a * 8 + r, n = wn * 32 + b * 8 + 2 * c;
+            if (hasa) {
+                V[n * TRSM4_LDV + (2 * grp) * NB + m] = acca[a][b][0];
+                V[(n + 1) * TRSM4_LDV + (2 * grp) * NB + m] = acca[a][b][1];
+            }
+            if (hasb) {
+                V[n * TRSM4_LDV + (2 * grp + 1) * NB + m] = accb[a][b][0];
+                V[(n + 1) * TRSM4_LDV + (2 * grp + 1) * NB + m] = accb[a][b][1];
+            }
+        }
+    load_tile<false>(Bs, Wm + (size_t)(k * NB) * Np + k * NB, Np, tid, 256);
+    __syncthreads();
+    if (tid < NB) rd[tid] = 1.0 / Bs[tid * LDT + tid];
+    __syncthreads();
+    if (ibase + (tid >> 6) < nt) subst_lower(Bs, LDT, rd, V, TRSM4_LDV, tid);
+    __syncthreads();
+    if (hasa) {
+        double* dst = Wm + (size_t)(ia * NB) * Np + k * NB;
+        for (int e = tid4; e < NB * NB; e += 128) {
+            int m = e >> 6, n = e & 63;
+            dst[(size_t)m * Np + n] = V[n * TRSM4_LDV + (2 * grp) * NB + m];
+        }
+    }
+    if (hasb) {
+        double* dst = Wm + (size_t)(ib * NB) * Np + k * NB;
+        for (int e = tid4; e < NB * NB; e += 128) {
+            int m = e >> 6, n = e & 63;
+            dst[(size_t)m * Np + n] = V[n * TRSM4_LDV + (2 * grp + 1) * NB + m];
+        }
+    }
+}
+
 // Trailing update after tile columns [kb, ke): A_ij -= sum_{k=kb}^{ke-1} L_ik L_jk^T for ke <= j <= i (64x64 tiles).
 // grid = (n(n+1)/2 with n = nt-ke, nmat), block = 128 (2x2 warps, 32x32 each).  Dynamic shared memory 2*TILE_SMEM.
 __global__ void __launch_bounds__(128) syrk_update_kernel(double* __restrict__ W, const int* __restrict__ ids, int Np,
                                                           int kb, int ke) {
+    GPRN_TRACE_SCOPE(TK_SYRK64);
     extern __shared__ double smem[];
     double* As = smem;
     double* Bs = smem + NB * LDT;
@@ -185,6 +342,7 @@ __global__ void __launch_bounds__(128) syrk_update_kernel(double* __restrict__ W
 #define TRTRI_DIAG_SMEM ((NB * LDT + NB * LDV + NB) * sizeof(double))
 __global__ void __launch_bounds__(64) trtri_diag_kernel(double* __restrict__ X, const double* __restrict__ W,
                                                         const int* __restrict__ ids, int Np) {
+    GPRN_TRACE_SCOPE(TK_TRTRI_DIAG);
     extern __shared__ double smem[];
     double* Ls = smem;
     double* V = smem + NB * LDT;
@@ -207,6 +365,7 @@ __global__ void __launch_bounds__(64) trtri_diag_kernel(double* __restrict__ X, 
 #define TRTRI_SMEM (2 * TILE_SMEM + (NB * LDV + NB) * sizeof(double))
 __global__ void __launch_bounds__(128) trtri_row_kernel(double* __restrict__ X, const double* __restrict__ W,
                                                         const int* __restrict__ ids, int Np, int i) {
+    GPRN_TRACE_SCOPE(TK_TRTRI_ROW);
     extern __shared__ double smem[];
     double* As = smem;
     double* Bs = smem + NB * LDT;
@@ -266,6 +425,7 @@ __global__ void __launch_bounds__(128) trtri_row_kernel(double* __restrict__ X, 
 // grid = (tiles, nmat), block = G_THREADS, dynamic smem GEMM128_SMEM.
 __global__ void __launch_bounds__(G_THREADS) syrk_outer_kernel(double* __restrict__ W, const int* __restrict__ ids,
                                                                int Np, int c0, int KB, int t0, int jcols) {
+    GPRN_TRACE_SCOPE(TK_SYRK_OUTER);
     extern __shared__ double smem[];
     int TI, TJ;
     if (jcols == 0) {
@@ -321,6 +481,7 @@ __host__ __forceinline__ int trtri_outer_units(int R0, int kc) {
 __global__ void __launch_bounds__(G_THREADS) trtri_outer_kernel(double* __restrict__ X, const double* __restrict__ W,
                                                                 double* __restrict__ Gp, const int* __restrict__ ids,
                                                                 int Np, int R0, int units, int kc) {
+    GPRN_TRACE_SCOPE(TK_TRTRI_OUTER);
     extern __shared__ double smem[];
     const int half = blockIdx.x / units;
     int u = blockIdx.x % units, n0 = 0, s = 0;
@@ -360,6 +521,7 @@ __global__ void __launch_bounds__(G_THREADS) trtri_outer_kernel(double* __restri
 __global__ void __launch_bounds__(128) trtri_inblock_kernel(double* __restrict__ X, const double* __restrict__ W,
                                                             const double* __restrict__ Gp, const int* __restrict__ ids,
                                                             int Np, int i0, int kc) {
+    GPRN_TRACE_SCOPE(TK_TRTRI_INBLOCK);
     extern __shared__ double smem[];
     double* As = smem;
     double* Bs = smem + NB * LDT;
@@ -439,6 +601,7 @@ __global__ void __launch_bounds__(128) trtri_inblock_kernel(double* __restrict__
 __global__ void __launch_bounds__(256) trmv_lower_kernel(double* __restrict__ z, const double* __restrict__ X,
                                                          const double* __restrict__ v, const int* __restrict__ ids,
                                                          const int* __restrict__ xids, int Np) {
+    GPRN_TRACE_SCOPE(TK_TRMV_LOWER);
     const int id = ids[blockIdx.y];
     const int xid = xids ? xids[blockIdx.y] : id;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -458,6 +621,7 @@ __global__ void __launch_bounds__(256) trmv_upper_norm_kernel(double* __restrict
                                                               const double* __restrict__ X,
                                                               const double* __restrict__ z,
                                                               const int* __restrict__ ids, int Np) {
+    GPRN_TRACE_SCOPE(TK_TRMV_UPPER);
     __shared__ double su[4][NB], sg[4][NB];
     const int id = ids[blockIdx.y];
     const int ct = blockIdx.x, n = ct * NB + (threadIdx.x & 63), rg = threadIdx.x >> 6;

@@ -56,6 +56,29 @@ static void prof_tick(int line) {
                         ":" + std::to_string(__LINE__) + ")");                                          \
     } while (0)
 
+// Launch with a per-launch priority (cudaLaunchAttributePriority): the latency-bound panel / in-block kernels of one
+// stream group are dispatched ahead of the pending CTAs of another group's wide GEMM launch.
+static int g_prio_hi = 0, g_prio_mode = -1;
+template <typename... KArgs, typename... Args>
+static void launch_hi(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    if (g_prio_mode < 0) {
+        int lo = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &g_prio_hi);
+        g_prio_mode = getenv("GPRN_PANEL_PRIO") ? atoi(getenv("GPRN_PANEL_PRIO")) : 1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributePriority;
+    at[0].val.priority = g_prio_hi;
+    cfg.attrs = at;
+    cfg.numAttrs = g_prio_mode ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -136,6 +159,8 @@ static bool g_attr_done = false;
 static int set_kernel_attrs() {
     if (g_attr_done) return 0;
     CU(cudaFuncSetAttribute(panel_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
+    CU(cudaFuncSetAttribute(potrf_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_COL_SMEM));
+    CU(cudaFuncSetAttribute(trsm_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_COL_SMEM));
     CU(cudaFuncSetAttribute(syrk_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(trtri_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
     CU(cudaFuncSetAttribute(trtri_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_DIAG_SMEM));
@@ -332,8 +357,22 @@ static int factor_batch(gprn_handle* h, double* W, const int* d_ids, int nmat, d
         const int ke = std::min(k0 + 4, nt);
         for (int k = k0; k < ke; k++) {
             const int n = nt - k - 1;
-            panel_col_kernel<<<dim3(std::max(1, (n + 1) / 2), nmat), 256, PANEL_SMEM, st>>>(W, d_ids, Np, k, k0, logdet, mstatus, ctr);
-            LAUNCH_CHECK(h);
+            // One launch per panel step (fused: shortest dependency chain) while the GPU is latency bound; two
+            // launches (potrf + 4-tile trsm: a third of the SM time) once enough matrices are in flight for the
+            // SMs to be the bottleneck.  Measured crossover (B200): nmat * nt^2 ~ 65536.  GPRN_FUSED_PANEL=0/1 forces.
+            static const int fused_env = getenv("GPRN_FUSED_PANEL") ? atoi(getenv("GPRN_FUSED_PANEL")) : -1;
+            const bool fused_panel = fused_env >= 0 ? fused_env != 0 : (size_t)nmat_concurrent * nt * nt < 65536;
+            if (fused_panel) {
+                launch_hi(panel_col_kernel, dim3(std::max(1, (n + 1) / 2), nmat), dim3(256), PANEL_SMEM, st, W, d_ids, Np, k, k0, logdet, mstatus, ctr);
+                LAUNCH_CHECK(h);
+            } else {
+                launch_hi(potrf_col_kernel, dim3(nmat), dim3(256), POTRF_COL_SMEM, st, W, d_ids, Np, k, k0, logdet, mstatus);
+                LAUNCH_CHECK(h);
+                if (n > 0) {
+                    launch_hi(trsm_col_kernel, dim3((n + 3) / 4, nmat), dim3(256), TRSM_COL_SMEM, st, W, d_ids, Np, k, k0);
+                    LAUNCH_CHECK(h);
+                }
+            }
         }
         if (ke < nt) {
             if (two) {
@@ -355,7 +394,7 @@ static int factor_batch(gprn_handle* h, double* W, const int* d_ids, int nmat, d
         }
     }
     if (X) {
-        trtri_diag_kernel<<<dim3(nt, nmat), 64, TRTRI_DIAG_SMEM, st>>>(X, W, d_ids, Np);
+        launch_hi(trtri_diag_kernel, dim3(nt, nmat), dim3(64), TRTRI_DIAG_SMEM, st, X, W, d_ids, Np);
         LAUNCH_CHECK(h);
         if (two || nt <= 4) {
             for (int i0 = 0; i0 < nt; i0 += 4) {
@@ -370,7 +409,7 @@ static int factor_batch(gprn_handle* h, double* W, const int* d_ids, int nmat, d
                 }
                 const int ncol = std::min(i0 + 4, nt) - 1;
                 if (ncol > 0) {
-                    trtri_inblock_kernel<<<dim3(ncol, nmat), 128, TRTRI_SMEM, st>>>(X, W, two ? Gp : nullptr, d_ids, Np, i0, kc);
+                    launch_hi(trtri_inblock_kernel, dim3(ncol, nmat), dim3(128), TRTRI_SMEM, st, X, W, two ? Gp : nullptr, d_ids, Np, i0, kc);
                     LAUNCH_CHECK(h);
                 }
             }
@@ -985,6 +1024,41 @@ extern "C" int gprn_sample(gprn_handle* h, const double* hyper, const double* z,
                         " (raise the nugget or add a WhiteNoise term)");
     return 0;
 }
+
+#ifdef GPRN_TRACE
+// Development-only entry points of the -DGPRN_TRACE build (tools/trace_run.py); not part of the C ABI.
+static TraceRec* g_trace_dev = nullptr;
+static unsigned g_trace_cap_host = 0;
+extern "C" int gprn_trace_begin(unsigned cap) {
+    if (!g_trace_dev || cap > g_trace_cap_host) {
+        if (g_trace_dev) cudaFree(g_trace_dev);
+        CU(cudaMalloc(&g_trace_dev, sizeof(TraceRec) * (size_t)cap));
+        g_trace_cap_host = cap;
+    }
+    unsigned zero = 0;
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyToSymbol(g_trace_buf, &g_trace_dev, sizeof(g_trace_dev)));
+    CU(cudaMemcpyToSymbol(g_trace_cap, &g_trace_cap_host, sizeof(unsigned)));
+    CU(cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(unsigned)));
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+extern "C" int gprn_trace_dump(const char* path) {
+    CU(cudaDeviceSynchronize());
+    unsigned n = 0;
+    CU(cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(unsigned)));
+    if (n > g_trace_cap_host) n = g_trace_cap_host;
+    std::vector<TraceRec> recs(n);
+    if (n) CU(cudaMemcpy(recs.data(), g_trace_dev, sizeof(TraceRec) * (size_t)n, cudaMemcpyDeviceToHost));
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail("gprn_trace_dump: cannot open file");
+    fwrite(recs.data(), sizeof(TraceRec), n, f);
+    fclose(f);
+    TraceRec* none = nullptr;
+    CU(cudaMemcpyToSymbol(g_trace_buf, &none, sizeof(none)));
+    return (int)n;
+}
+#endif
 
 extern "C" int64_t gprn_launch_count(gprn_handle* h) { return h ? h->launches : 0; }
 extern "C" int gprn_reset_launch_count(gprn_handle* h) {

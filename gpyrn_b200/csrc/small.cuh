@@ -40,6 +40,7 @@ __device__ __forceinline__ double* small_tile(double* scratch, int I, int J) {
 }
 
 __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
+    GPRN_TRACE_SCOPE(TK_SMALL);
     extern __shared__ double smem[];
     double* Bs = smem;                 // B operand / potrf input+output (L_kk) / A operand in the inverse
     double* As0 = smem + NB * LDT;
