@@ -14,7 +14,9 @@
 #define NB 64           // tile size
 #define LDT 68          // shared-memory row stride (doubles) of an MMA operand tile: 68*8 B = 32 (mod 128)
                         // -> the m8n8k4 fragment loads of a half-warp hit 16 distinct 8-byte slots
-#define LDV 65          // odd stride for tiles accessed one-vector-per-thread (conflict free both ways)
+#define LDV 68          // substitution vectors V[elem][vec]: stride = 4 (mod 16) doubles, so the DMMA B-fragment loads of
+#define LDV2 132        // subst_lower_mma (lane (r,c) -> element 4c.., vector r) hit 16 distinct 8-byte slots per half-warp
+#define LDV4 260        // (LDV2 / LDV4: two / four tiles of vectors side by side)
 #define TILE_SMEM (NB * LDT * sizeof(double))
 
 namespace gprn {
@@ -111,6 +113,74 @@ __device__ __forceinline__ void subst_lower(const double* __restrict__ Ls, int l
         }
 #pragma unroll
         for (int u = 0; u < 8; u++) V[(mb * 8 + u) * ldv + n] = y[u];
+    }
+}
+
+// Warp-cooperative forward substitution  L y = g  for the 8*NT vectors vec0 .. vec0+8*NT-1 (element m of vector n at
+// V[m*ldv + n], ldv = 4 mod 16), called by all 32 lanes of a warp; different warps take different vector ranges and
+// never synchronise with each other.  Blocked by 8 like subst_lower, but the off-diagonal part
+//     Y[8 rows of block mb][vectors] -= L[mb][kb] (8x8) * X[kb][vectors]
+// runs on DMMA m8n8k4 (2 k-steps per 8x8 block and 8-vector tile; accumulator = the warp's 8 x 8NT slab of V), and
+// only the 8x8 diagonal blocks are solved by scalar FMA chains, one vector per lane.  Still a genuine substitution:
+// no inverse of L or of its diagonal blocks is formed.  first_block as in subst_lower (all vectors of the warp).
+template <int NT>
+__device__ __forceinline__ void subst_lower_mma(const double* __restrict__ Ls, int lds, const double* __restrict__ rd,
+                                                double* V, int ldv, int vec0, int first_block = 0) {
+    const int lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
+    constexpr int NV = (8 * NT + 31) / 32;          // vectors per lane in the diagonal solves
+    for (int mb = first_block; mb < 8; mb++) {
+        double acc[NT][2];
+        double* vrow = V + (mb * 8 + r) * ldv + vec0 + 2 * c;
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            acc[t][0] = vrow[8 * t];
+            acc[t][1] = vrow[8 * t + 1];
+        }
+        const double* lrow = Ls + (mb * 8 + r) * lds + c;
+        for (int kb = first_block; kb < mb; kb++) {
+            const double a0 = -lrow[kb * 8], a1 = -lrow[kb * 8 + 4];
+            const double* xb = V + (kb * 8 + c) * ldv + vec0 + r;
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+                dmma884(acc[t], a0, xb[8 * t]);
+                dmma884(acc[t], a1, xb[4 * ldv + 8 * t]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            vrow[8 * t] = acc[t][0];
+            vrow[8 * t + 1] = acc[t][1];
+        }
+        __syncwarp();
+        double y[NV][8];
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            const int v = lane + 32 * j;
+            if (v < 8 * NT) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) y[j][u] = V[(mb * 8 + u) * ldv + vec0 + v];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const double* ld = Ls + (mb * 8 + u) * lds + mb * 8;
+            const double rdu = rd[mb * 8 + u];
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+#pragma unroll
+                for (int w = 0; w < u; w++) y[j][u] = fma(-ld[w], y[j][w], y[j][u]);
+                y[j][u] = y[j][u] * rdu;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            const int v = lane + 32 * j;
+            if (v < 8 * NT) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) V[(mb * 8 + u) * ldv + vec0 + v] = y[j][u];
+            }
+        }
+        __syncwarp();
     }
 }
 

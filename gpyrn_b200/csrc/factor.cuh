@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) form_a_kernel(double* __restrict__ W, con
 // and raises status[id] on a non-positive pivot.
 // grid = (max(1, ceil((nt-k-1)/2)), nmat), block = 256 (warps 0-3: diagonal + row tile i0, warps 4-7: i0+1).
 #define PANEL_SMEM ((3 * NB * LDT + 4 * NB) * sizeof(double))
-#define TRSM_LDV 129
+#define TRSM_LDV LDV2
 __global__ void __launch_bounds__(256) panel_col_kernel(double* __restrict__ W, const int* __restrict__ ids, int Np,
                                                         int k, int k0, double* __restrict__ logdet,
                                                         int* __restrict__ status, int* __restrict__ ctr) {
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) panel_col_kernel(double* __restrict__ W, 
         if (last) ctr[id] = 0;
     }
     potrf64(Bs, LDV, Bs, rd, col, pivs, &bad);
-    if (tid < 2 * NB && (k + 1 + 2 * (int)blockIdx.x + (tid >> 6)) < nt) subst_lower(Bs, LDT, rd, V, TRSM_LDV, tid);
+    if (k + 1 + 2 * (int)blockIdx.x + grp < nt) subst_lower_mma<2>(Bs, LDT, rd, V, TRSM_LDV, grp * NB + w4 * 16);
     __syncthreads();
     if (has) {
         double* dst = Wm + (size_t)(i_own * NB) * Np + k * NB;
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) potrf_col_kernel(double* __restrict__ W, 
 // trsm_col_kernel: L_ik = (A_ik - sum_{k'} L_ik' L_kk'^T) L_kk^-T for the row tiles i = k+1+4*blockIdx.x .. +3.
 // Warps 0-3 own the first two tiles, warps 4-7 the other two (one accumulator set each).
 // grid = (ceil((nt-k-1)/4), nmat), block = 256, dynamic smem TRSM_COL_SMEM.
-#define TRSM4_LDV 257
+#define TRSM4_LDV LDV4
 #define TRSM_COL_SMEM ((5 * NB * LDT + NB) * sizeof(double))
 __global__ void __launch_bounds__(256) trsm_col_kernel(double* __restrict__ W, const int* __restrict__ ids, int Np,
                                                        int k, int k0) {
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256) trsm_col_kernel(double* __restrict__ W, c
     __syncthreads();
     if (tid < NB) rd[tid] = 1.0 / Bs[tid * LDT + tid];
     __syncthreads();
-    if (ibase + (tid >> 6) < nt) subst_lower(Bs, LDT, rd, V, TRSM4_LDV, tid);
+    if (ibase + (warp >> 1) < nt) subst_lower_mma<4>(Bs, LDT, rd, V, TRSM4_LDV, (warp >> 1) * NB + (warp & 1) * 32);
     __syncthreads();
     if (hasa) {
         double* dst = Wm + (size_t)(ia * NB) * Np + k * NB;
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(64) trtri_diag_kernel(double* __restrict__ X, 
     __syncthreads();
     rd[tid] = 1.0 / Ls[tid * LDT + tid];
     __syncthreads();
-    subst_lower(Ls, LDT, rd, V, LDV, tid, tid >> 3);
+    subst_lower_mma<4>(Ls, LDT, rd, V, LDV, (tid >> 5) * 32, (tid >> 5) * 4);
     __syncthreads();
     double* Xt = X + off;
     for (int m = 0; m < NB; m++) Xt[(size_t)m * Np + tid] = V[m * LDV + tid];
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(128) trtri_row_kernel(double* __restrict__ X, 
     double* rd = V + NB * LDV;
     if (tid < NB) rd[tid] = 1.0 / As[tid * LDT + tid];
     __syncthreads();
-    if (tid < NB) subst_lower(As, LDT, rd, V, LDV, tid);
+    subst_lower_mma<2>(As, LDT, rd, V, LDV, warp * 16);
     __syncthreads();
     double* Xt = Xm + (size_t)(i * NB) * Np + j * NB;
     for (int e = tid; e < NB * NB; e += 128) {
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(128) trtri_inblock_kernel(double* __restrict__
         double* rd = V + NB * LDV;
         if (tid < NB) rd[tid] = 1.0 / As[tid * LDT + tid];
         __syncthreads();
-        if (tid < NB) subst_lower(As, LDT, rd, V, LDV, tid);
+        subst_lower_mma<2>(As, LDT, rd, V, LDV, warp * 16);
         __syncthreads();
         for (int e = tid; e < NB * NB; e += 128) {
             int m = e >> 6, n = e & 63;
