@@ -1,6 +1,7 @@
 """Per-CTA execution trace of one batched ELBO call (development aid; run on the GPU box).
 
     python tools/trace_run.py N p q NODE B MAX_ITER [out.npz]
+    python tools/trace_run.py --analyse out.npz          (analysis only, no GPU)
 
 Builds a second library with -DGPRN_TRACE (gpyrn_b200/csrc/libgprn_b200_trace.so; every CTA of the factorisation
 kernels stamps %globaltimer / %smid), runs one warm-up call and one traced call, and prints where the SM time of the
@@ -44,25 +45,39 @@ def analyse(rec, nsm=148):
     for k in sorted(set(rec["kid"].tolist())):
         m = rec["kid"] == k
         print(f"{NAMES.get(k, k):16s} {m.sum():8d} {100 * dur[m].sum() / tot:10.2f} {dur[m].mean():9.1f} {dur[m].max():9.1f}")
-    # time-resolved occupancy: number of SMs that hold >= 1 GEMM-class CTA / >= 1 other CTA, sampled on a 2 us grid
-    step = 2000
-    grid = np.arange(T0, T1, step)
-    sm_g = np.zeros((nsm, grid.size), dtype=bool)
-    sm_o = np.zeros((nsm, grid.size), dtype=bool)
-    for r0, r1, k, sm in zip(t0, t1, rec["kid"], rec["smid"]):
-        a, b = (r0 - T0) // step, (r1 - T0) // step + 1
-        (sm_g if k in GEMM else sm_o)[sm % nsm, a:b] = True
-    g = sm_g.mean()
-    o_only = (sm_o & ~sm_g).mean()
-    idle = (~sm_o & ~sm_g).mean()
-    print(f"SM-time: GEMM-class resident {100 * g:.1f} %, only latency-class resident {100 * o_only:.1f} %, idle {100 * idle:.1f} %")
-    ng = sm_g.sum(axis=0)
-    print("fraction of wall time with #SMs running GEMM-class CTAs: "
-          + ", ".join(f"{lo}-{hi}: {100 * np.mean((ng >= lo) & (ng <= hi)):.1f} %" for lo, hi in
+    # time-resolved occupancy on a 4 us grid: which kernel classes hold each SM
+    step = 4000
+    ng = int((T1 - T0) // step + 1)
+    kinds = sorted(set(rec["kid"].tolist()))
+    occ = {k: np.zeros((nsm, ng), dtype=bool) for k in kinds}
+    for k in kinds:
+        m = rec["kid"] == k
+        for a, b, sm in zip((t0[m] - T0) // step, (t1[m] - T0) // step + 1, rec["smid"][m] % nsm):
+            occ[k][sm, a:b] = True
+    g = np.zeros((nsm, ng), dtype=bool)
+    for k in kinds:
+        if k in GEMM:
+            g |= occ[k]
+    npres = sum(occ[k].astype(np.int8) for k in kinds if k not in GEMM)
+    lat = (~g) & (npres > 0)
+    print(f"SM-time with a GEMM-class CTA (syrk_outer / trtri_outer / cross_frob) resident: {100 * g.mean():.1f} %")
+    print("SM-time with only latency-class CTAs resident, attributed by kernel (equal split among those present):")
+    for k in kinds:
+        if k not in GEMM:
+            share = ((occ[k] & lat) / np.maximum(npres, 1)).sum() / (nsm * ng)
+            if share > 5e-4:
+                print(f"    {NAMES.get(k, k):14s} {100 * share:6.2f} %")
+    print(f"SM-time idle: {100 * ((~g) & (npres == 0)).mean():.1f} %")
+    nge = g.sum(axis=0)
+    print("fraction of wall time by number of SMs running GEMM-class CTAs: "
+          + ", ".join(f"{lo}-{hi}: {100 * np.mean((nge >= lo) & (nge <= hi)):.1f} %" for lo, hi in
                       ((0, 0), (1, 36), (37, 73), (74, 110), (111, 140), (141, 148))))
 
 
 def main():
+    if sys.argv[1] == "--analyse":
+        analyse(np.load(sys.argv[2])["rec"])
+        return
     N, p, q = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
     node, B, max_iter = sys.argv[4], int(sys.argv[5]), int(sys.argv[6])
     out = sys.argv[7] if len(sys.argv) > 7 else None
