@@ -422,39 +422,42 @@ __global__ void __launch_bounds__(128) trtri_row_kernel(double* __restrict__ X, 
 // two tile columns (the next 256-column panel).  The host applies slabs lazily -- after an even panel only the next
 // panel's columns are updated (KB = 256), after an odd panel everything to the right gets both slabs at once
 // (KB = 512) -- which halves the read-modify-write passes over the trailing matrix.
-// grid = (tiles, nmat), block = G_THREADS, dynamic smem GEMM128_SMEM.
-__global__ void __launch_bounds__(G_THREADS) syrk_outer_kernel(double* __restrict__ W, const int* __restrict__ ids,
+// A 128x128 tile is formed by G_SPLIT = 128 / G_BM CTAs (row slabs of G_BM rows; blockIdx.x = tile * G_SPLIT + slab).
+// grid = (G_SPLIT * tiles, nmat), block = G_THREADS, dynamic smem GEMM128_SMEM.
+#define G_SPLIT (128 / G_BM)
+__global__ void __launch_bounds__(G_THREADS, G_MINB) syrk_outer_kernel(double* __restrict__ W, const int* __restrict__ ids,
                                                                int Np, int c0, int KB, int t0, int jcols) {
     GPRN_TRACE_SCOPE(TK_SYRK_OUTER);
     extern __shared__ double smem[];
     int TI, TJ;
+    const int tile = blockIdx.x / G_SPLIT, slab = blockIdx.x % G_SPLIT;
     if (jcols == 0) {
-        tri_decode(blockIdx.x, TI, TJ);
+        tri_decode(tile, TI, TJ);
     } else {
-        const int n128 = (Np - t0) / G_BM;
-        if ((int)blockIdx.x < n128) { TI = blockIdx.x; TJ = 0; }
-        else { TI = blockIdx.x - n128 + 1; TJ = 1; }
+        const int n128 = (Np - t0) / 128;
+        if (tile < n128) { TI = tile; TJ = 0; }
+        else { TI = tile - n128 + 1; TJ = 1; }
     }
-    const int r0 = t0 + TI * G_BM, n0 = t0 + TJ * G_BN;
+    const int r0 = t0 + TI * 128 + slab * G_BM, n0 = t0 + TJ * G_BN;
     const int id = ids[blockIdx.y];
     double* Wm = W + (size_t)id * Np * Np;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp / G_WARPS_N, wn = warp % G_WARPS_N;
     const int r = lane >> 2, c = lane & 3;
     double* C = Wm + (size_t)r0 * Np + n0;
     // The products are summed on their own and subtracted from C once at the end: starting the accumulators at
     // -C (which would make the epilogue a pure store) rounds every partial sum at the magnitude of C and costs
     // measurable ELBO parity at N >= 2048 (c5 anchor: 1e-10 bar missed), for no gain in time.
-    double acc[G_MI][4][2];
+    double acc[G_MI][G_NI][2];
 #pragma unroll
     for (int i = 0; i < G_MI; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < G_NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
     gemm128_mainloop<false>(acc, smem, Wm + (size_t)r0 * Np + c0, Np, Wm + (size_t)n0 * Np + c0, Np, KB);
 #pragma unroll
     for (int i = 0; i < G_MI; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            double2* p = reinterpret_cast<double2*>(C + (size_t)(wm * G_WM + i * 8 + r) * Np + wn * 32 + j * 8 + 2 * c);
+        for (int j = 0; j < G_NI; j++) {
+            double2* p = reinterpret_cast<double2*>(C + (size_t)(wm * G_WM + i * 8 + r) * Np + wn * G_WN + j * 8 + 2 * c);
             double2 v = *p;
             v.x -= acc[i][j][0];
             v.y -= acc[i][j][1];
@@ -469,7 +472,7 @@ __global__ void __launch_bounds__(G_THREADS) syrk_outer_kernel(double* __restric
 // writes to X as before, chunk s >= 1 to the partial buffer Gp[id][s-1] (256 x Np strip, same row/column indexing);
 // the in-block kernel adds the partials in a fixed order (deterministic, no atomics).  With enough matrices in
 // flight the launch is already full and kc = R0 (no split) is faster: shorter K means more prologue / epilogue.
-// grid = (2 * trtri_outer_units(R0), nmat), block = G_THREADS, dynamic smem GEMM128_SMEM.
+// grid = ((256 / G_BM) * trtri_outer_units(R0), nmat), block = G_THREADS, dynamic smem GEMM128_SMEM.
 #define TRTRI_KC 1024
 #define TRTRI_MAXCH(Np) (((Np) + TRTRI_KC - 1) / TRTRI_KC)      // chunks of the longest tile
 __host__ __device__ __forceinline__ int trtri_nchunk(int R0, int n0, int kc) { return (R0 - n0 + kc - 1) / kc; }
@@ -478,12 +481,12 @@ __host__ __forceinline__ int trtri_outer_units(int R0, int kc) {
     for (int n0 = 0; n0 < R0; n0 += G_BN) u += trtri_nchunk(R0, n0, kc);
     return u;
 }
-__global__ void __launch_bounds__(G_THREADS) trtri_outer_kernel(double* __restrict__ X, const double* __restrict__ W,
+__global__ void __launch_bounds__(G_THREADS, G_MINB) trtri_outer_kernel(double* __restrict__ X, const double* __restrict__ W,
                                                                 double* __restrict__ Gp, const int* __restrict__ ids,
                                                                 int Np, int R0, int units, int kc) {
     GPRN_TRACE_SCOPE(TK_TRTRI_OUTER);
     extern __shared__ double smem[];
-    const int half = blockIdx.x / units;
+    const int half = blockIdx.x / units;          // row slab (G_BM rows) of the 256-row block
     int u = blockIdx.x % units, n0 = 0, s = 0;
     for (;; n0 += G_BN) {                      // decode (column tile, chunk)
         const int nc = trtri_nchunk(R0, n0, kc);
@@ -495,22 +498,22 @@ __global__ void __launch_bounds__(G_THREADS) trtri_outer_kernel(double* __restri
     const int id = ids[blockIdx.y];
     const double* Wm = W + (size_t)id * Np * Np;
     double* Xm = X + (size_t)id * Np * Np;
-    double acc[G_MI][4][2];
+    double acc[G_MI][G_NI][2];
 #pragma unroll
     for (int i = 0; i < G_MI; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < G_NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
     gemm128_mainloop<true>(acc, smem, Wm + (size_t)r0 * Np + k0, Np, Xm + (size_t)k0 * Np + n0, Np, k1 - k0);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp / G_WARPS_N, wn = warp % G_WARPS_N;
     const int r = lane >> 2, c = lane & 3;
     double* C = (s == 0) ? Xm + (size_t)r0 * Np + n0
                          : Gp + ((size_t)id * (TRTRI_MAXCH(Np) - 1) + (s - 1)) * OUTER_KB * Np + (size_t)(half * G_BM) * Np + n0;
 #pragma unroll
     for (int i = 0; i < G_MI; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < G_NI; j++) {
             double2 v = make_double2(-acc[i][j][0], -acc[i][j][1]);
-            *reinterpret_cast<double2*>(C + (size_t)(wm * G_WM + i * 8 + r) * Np + wn * 32 + j * 8 + 2 * c) = v;
+            *reinterpret_cast<double2*>(C + (size_t)(wm * G_WM + i * 8 + r) * Np + wn * G_WN + j * 8 + 2 * c) = v;
         }
 }
 

@@ -378,13 +378,13 @@ static int factor_batch(gprn_handle* h, double* W, const int* d_ids, int nmat, d
             if (two) {
                 // lazy trailing update (see syrk_outer_kernel): panel index pidx = k0 / 4
                 static const bool eager = getenv("GPRN_EAGER_SYRK") != nullptr;
-                const int pidx = k0 / 4, t0 = ke * NB, n128 = (Np - t0) / G_BM;
+                const int pidx = k0 / 4, t0 = ke * NB, n128 = (Np - t0) / 128;
                 if (eager) {
-                    syrk_outer_kernel<<<dim3(n128 * (n128 + 1) / 2, nmat), G_THREADS, GEMM128_SMEM, st>>>(W, d_ids, Np, k0 * NB, OUTER_KB, t0, 0);
+                    syrk_outer_kernel<<<dim3(G_SPLIT * n128 * (n128 + 1) / 2, nmat), G_THREADS, GEMM128_SMEM, st>>>(W, d_ids, Np, k0 * NB, OUTER_KB, t0, 0);
                 } else if (pidx % 2 == 0) {
-                    syrk_outer_kernel<<<dim3(2 * n128 - 1, nmat), G_THREADS, GEMM128_SMEM, st>>>(W, d_ids, Np, k0 * NB, OUTER_KB, t0, 2);
+                    syrk_outer_kernel<<<dim3(G_SPLIT * (2 * n128 - 1), nmat), G_THREADS, GEMM128_SMEM, st>>>(W, d_ids, Np, k0 * NB, OUTER_KB, t0, 2);
                 } else {
-                    syrk_outer_kernel<<<dim3(n128 * (n128 + 1) / 2, nmat), G_THREADS, GEMM128_SMEM, st>>>(W, d_ids, Np, (k0 - 4) * NB, 2 * OUTER_KB, t0, 0);
+                    syrk_outer_kernel<<<dim3(G_SPLIT * n128 * (n128 + 1) / 2, nmat), G_THREADS, GEMM128_SMEM, st>>>(W, d_ids, Np, (k0 - 4) * NB, 2 * OUTER_KB, t0, 0);
                 }
             } else {
                 const int n = nt - ke;
@@ -404,7 +404,7 @@ static int factor_batch(gprn_handle* h, double* W, const int* d_ids, int nmat, d
                     static const bool no_split = getenv("GPRN_NO_SPLITK") != nullptr;
                     kc = (no_split || nmat_concurrent * 2 * (i0 * NB / G_BN) >= 2 * h->num_sms) ? std::max(i0 * NB, TRTRI_KC) : TRTRI_KC;
                     const int units = trtri_outer_units(i0 * NB, kc);
-                    trtri_outer_kernel<<<dim3(2 * units, nmat), G_THREADS, GEMM128_SMEM, st>>>(X, W, Gp, d_ids, Np, i0 * NB, units, kc);
+                    trtri_outer_kernel<<<dim3((OUTER_KB / G_BM) * units, nmat), G_THREADS, GEMM128_SMEM, st>>>(X, W, Gp, d_ids, Np, i0 * NB, units, kc);
                     LAUNCH_CHECK(h);
                 }
                 const int ncol = std::min(i0 + 4, nt) - 1;
@@ -1041,6 +1041,17 @@ extern "C" int gprn_trace_begin(unsigned cap) {
     CU(cudaMemcpyToSymbol(g_trace_cap, &g_trace_cap_host, sizeof(unsigned)));
     CU(cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(unsigned)));
     CU(cudaDeviceSynchronize());
+    return 0;
+}
+extern "C" int gprn_trace_small_phases(unsigned long long* out12, int reset) {
+    CU(cudaDeviceSynchronize());
+    unsigned long long tmp[16];
+    CU(cudaMemcpyFromSymbol(tmp, g_small_phase, sizeof(tmp)));
+    for (int i = 0; i < 12; i++) out12[i] = tmp[i];
+    if (reset) {
+        memset(tmp, 0, sizeof(tmp));
+        CU(cudaMemcpyToSymbol(g_small_phase, tmp, sizeof(tmp)));
+    }
     return 0;
 }
 extern "C" int gprn_trace_dump(const char* path) {

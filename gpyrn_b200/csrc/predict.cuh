@@ -75,31 +75,31 @@ __global__ void __launch_bounds__(128) predict_norm_kernel(double* __restrict__ 
     if (tid < NB) rownorm2[blockIdx.x * NB + tid] = rs[0][tid] + rs[1][tid];
 }
 
-// Large-N variant of predict_norm_kernel on the 128x128 DMMA GEMM core: CTA (tt, at) forms the tile
-// C[t][a] = sum_{n <= a} Ks[t][n] X[a][n] for 128 test epochs x 128 rows of X (K = a0 + 128, X lower triangular),
+// Large-N variant of predict_norm_kernel on the DMMA GEMM core (gemm128.cuh): CTA (tt, at) forms the tile
+// C[t][a] = sum_{n <= a} Ks[t][n] X[a][n] for G_BM test epochs x 128 rows of X (K = a0 + 128, X lower triangular),
 // squares it and writes the 128 row sums to partial[at][t]; predict_var_kernel adds the partials in tile order.
-// Ks: [Tpad][Np] with zero padding (columns >= N, rows >= T).  grid = (Tpad/128, Np/128), block = G_THREADS,
+// Ks: [Tpad][Np] with zero padding (columns >= N, rows >= T).  grid = (Tpad/G_BM, Np/128), block = G_THREADS,
 // dynamic smem GEMM128_SMEM.  blockIdx.y is mapped to descending a so that the long-K tiles start first.
-__global__ void __launch_bounds__(G_THREADS) predict_norm128_kernel(double* __restrict__ partial, int Tpad,
+__global__ void __launch_bounds__(G_THREADS, G_MINB) predict_norm128_kernel(double* __restrict__ partial, int Tpad,
                                                                     const double* __restrict__ Ks,
                                                                     const double* __restrict__ X, int Np) {
     extern __shared__ double smem[];
     __shared__ double rs[G_WARPS_N][G_BM];
     const int na = Np / G_BN;
     const int at = na - 1 - blockIdx.y, a0 = at * G_BN, t0 = blockIdx.x * G_BM;
-    double acc[G_MI][4][2];
+    double acc[G_MI][G_NI][2];
 #pragma unroll
     for (int i = 0; i < G_MI; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < G_NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
     gemm128_mainloop<false>(acc, smem, Ks + (size_t)t0 * Np, Np, X + (size_t)a0 * Np, Np, a0 + G_BN);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp / G_WARPS_N, wn = warp % G_WARPS_N;
     const int r = lane >> 2, c = lane & 3;
 #pragma unroll
     for (int i = 0; i < G_MI; i++) {
         double sr = 0.0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < G_NI; j++) {
             sr = fma(acc[i][j][0], acc[i][j][0], sr);
             sr = fma(acc[i][j][1], acc[i][j][1], sr);
         }
@@ -110,7 +110,10 @@ __global__ void __launch_bounds__(G_THREADS) predict_norm128_kernel(double* __re
     __syncthreads();
     if (threadIdx.x < G_BM) {
         const int t = threadIdx.x;
-        partial[(size_t)at * Tpad + t0 + t] = (rs[0][t] + rs[1][t]) + (rs[2][t] + rs[3][t]);
+        double sp = rs[0][t];
+#pragma unroll
+        for (int w = 1; w < G_WARPS_N; w++) sp += rs[w][t];
+        partial[(size_t)at * Tpad + t0 + t] = sp;
     }
 }
 

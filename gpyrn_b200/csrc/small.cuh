@@ -22,6 +22,21 @@ namespace gprn {
 // 3 operand tiles + col(128) + pivs(64) + rd(64) + gacc(256) + zacc(256) + vloc(256)
 #define SMALL_SMEM ((3 * NB * LDT + 4 * NB + 3 * SMALL_MAX_NT * NB) * sizeof(double))
 
+#ifdef GPRN_TRACE
+__device__ unsigned long long g_small_phase[16];
+#define SMALL_PH(i)                                                        \
+    do {                                                                   \
+        if (threadIdx.x == 0) {                                            \
+            long long t_ = clock64();                                      \
+            ph_acc[ph_cur] += (unsigned long long)(t_ - ph_last);          \
+            ph_last = t_;                                                  \
+            ph_cur = (i);                                                  \
+        }                                                                  \
+    } while (0)
+#else
+#define SMALL_PH(i)
+#endif
+
 struct SmallArgs {
     const double* K;       // [.][Np][Np] assembled covariance matrices (lower tiles)
     const int* ids;        // matrix ids
@@ -59,6 +74,11 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
     const int grp = warp >> 2, w4 = warp & 3, wm = w4 >> 1, wn = w4 & 1, tid4 = tid & 127;
     const int r = lane >> 2, c = lane & 3;
     double* sc = a.scratch + (size_t)blockIdx.x * SMALL_SCRATCH_DOUBLES;
+#ifdef GPRN_TRACE
+    unsigned long long ph_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long ph_last = clock64();
+    int ph_cur = 0;
+#endif
 
     for (int mi = blockIdx.x; mi < a.nmat; mi += gridDim.x) {
         const int id = a.ids[mi];
@@ -75,6 +95,7 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
             for (int s = 0; s < 2 && k + 2 * s < nt; s++) {
                 const int it = k + 2 * s + grp;
                 const bool have = it < nt;
+                SMALL_PH(1);
                 double acc[4][4][2];
 #pragma unroll
                 for (int x = 0; x < 4; x++)
@@ -93,6 +114,7 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
                         acc[x][y][1] = v.y;
                     }
                 const bool diag = (s == 0 && grp == 0);
+                SMALL_PH(2);
                 for (int kp = 0; kp < k; kp++) {
                     load_tile<false>(Bs, small_tile(sc, k, kp), NB, tid, 256);
                     if (have && !diag) load_tile<false>(grp ? As1 : As0, small_tile(sc, it, kp), NB, tid4, 128);
@@ -100,6 +122,7 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
                     if (have) mma_tile<true>(acc, diag ? Bs : (grp ? As1 : As0), Bs, wm, wn, lane);
                     __syncthreads();
                 }
+                SMALL_PH(3);
                 if (s == 0) {
 #pragma unroll
                     for (int x = 0; x < 4; x++)
@@ -115,10 +138,13 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
                             }
                         }
                     __syncthreads();
+                    SMALL_PH(4);
                     potrf64(Bs, SMALL_LDP, Bs, rd, col, pivs, &bad);
+                    SMALL_PH(5);
                     if (tid >= NB && tid < 2 * NB && k + 1 < nt) subst_lower(Bs, LDT, rd, V, SMALL_LDV, tid);
                     if (tid < 32) logsum += log(pivs[tid]) + log(pivs[tid + 32]);
                     __syncthreads();
+                    SMALL_PH(6);
                     double* dkk = small_tile(sc, k, k);
                     for (int e = tid; e < NB * NB; e += 256) dkk[e] = Bs[(e >> 6) * LDT + (e & 63)];
                     if (k + 1 < nt) {
@@ -140,8 +166,10 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
                     __syncthreads();
                     if (tid < NB) rd[tid] = 1.0 / Bs[tid * LDT + tid];
                     __syncthreads();
+                    SMALL_PH(5);
                     if (tid < 2 * NB && k + 2 + (tid >> 6) < nt) subst_lower(Bs, LDT, rd, V, SMALL_LDV, tid);
                     __syncthreads();
+                    SMALL_PH(6);
                     if (have) {
                         double* d2 = small_tile(sc, it, k);
                         for (int e = tid4; e < NB * NB; e += 128) d2[e] = V[(e & 63) * SMALL_LDV + grp * NB + (e >> 6)];
@@ -157,6 +185,7 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
                 if (bad) a.mstatus[id] = 1;
             }
         }
+        SMALL_PH(0);
         if (!a.do_inverse) continue;
 
         // ================= inverse by block rows; X tiles overwrite the L tiles =================
@@ -169,6 +198,7 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
         for (int i = 0; i < nt; i++) {
             for (int j0 = 0; j0 <= i; j0 += 2) {
                 const int j = j0 + grp;                 // this group's right-hand-side tile (j == i: identity)
+                SMALL_PH(7);
                 double acc[4][4][2];
 #pragma unroll
                 for (int x = 0; x < 4; x++)
@@ -182,6 +212,7 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
                     if (part) mma_tile<true>(acc, Bs, grp ? As1 : As0, wm, wn, lane);
                     __syncthreads();
                 }
+                SMALL_PH(8);
                 // stage right-hand sides: vector = column n of the tile, element m at V[m*ldv + grp*64 + n]
                 if (j < i) {
 #pragma unroll
@@ -200,8 +231,10 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
                 if (tid < NB) rd[tid] = 1.0 / Bs[tid * LDT + tid];
                 __syncthreads();
                 const int jt = j0 + (tid >> 6);          // tile handled by thread tid < 128 in the substitution
+                SMALL_PH(9);
                 if (tid < 2 * NB && jt <= i) subst_lower(Bs, LDT, rd, V, SMALL_LDV, tid, jt == i ? ((tid & 63) >> 3) : 0);
                 __syncthreads();
+                SMALL_PH(10);
                 if (tid < 2 * NB && jt <= i) {
                     // column sums of squares of X_ij (thread = column) -> g_j ; single writer per (j, n) and round
                     double sg = 0.0;
@@ -226,6 +259,7 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
                 __syncthreads();
             }
         }
+        SMALL_PH(11);
         // u_j[n] = sum_{i >= j} sum_m X_ij[m][n] z_i[m]   (X tiles from the L2-resident scratch)
         {
             const int j = tid >> 6, n = tid & 63;
@@ -240,7 +274,12 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
             }
         }
         __syncthreads();
+        SMALL_PH(0);
     }
+#ifdef GPRN_TRACE
+    if (threadIdx.x == 0)
+        for (int i = 0; i < 12; i++) atomicAdd(&g_small_phase[i], ph_acc[i]);
+#endif
 }
 
 }  // namespace gprn

@@ -104,6 +104,15 @@ def main():
     path = os.path.join(ROOT, "gpurun_out", "trace.bin")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     n = L.gprn_trace_dump(path.encode())
+    ph = (ctypes.c_ulonglong * 12)()
+    L.gprn_trace_small_phases(ph, 0)
+    if sum(ph):
+        names = ["other/loop", "chol: load A tiles", "chol: MMA update", "chol: stage", "chol: potrf64", "chol: subst",
+                 "chol: store L", "inv: MMA", "inv: stage + L_ii", "inv: subst", "inv: g/z sums + store X", "u pass"]
+        tot = float(sum(ph))
+        print("fused small kernel, thread-0 clock64 share by phase (warm-up + traced call):")
+        for nm, v in zip(names, ph):
+            print(f"    {nm:26s} {100 * v / tot:6.2f} %")
     rec = np.fromfile(path, dtype=np.dtype([("t0", "<u8"), ("t1", "<u8"), ("kid", "<i4"), ("smid", "<i4")]))
     print(f"{n} records, device time {L.gprn_last_elbo_ms(g._h()):.1f} ms")
     analyse(rec)
