@@ -211,26 +211,30 @@ __global__ void __launch_bounds__(256) potrf_col_kernel(double* __restrict__ W, 
     }
 }
 
-// trsm_col_kernel: L_ik = (A_ik - sum_{k'} L_ik' L_kk'^T) L_kk^-T for the row tiles i = k+1+4*blockIdx.x .. +3.
-// Warps 0-3 own the first two tiles, warps 4-7 the other two (one accumulator set each).
-// grid = (ceil((nt-k-1)/4), nmat), block = 256, dynamic smem TRSM_COL_SMEM.
-#define TRSM4_LDV LDV4
-#define TRSM_COL_SMEM ((5 * NB * LDT + NB) * sizeof(double))
-__global__ void __launch_bounds__(256) trsm_col_kernel(double* __restrict__ W, const int* __restrict__ ids, int Np,
-                                                       int k, int k0) {
+// trsm_col_kernel<GROUPS>: L_ik = (A_ik - sum_{k'} L_ik' L_kk'^T) L_kk^-T for the 2*GROUPS row tiles
+// i = k+1 + 2*GROUPS*blockIdx.x ...  Each group of 4 warps owns two tiles (one accumulator set each).
+// GROUPS = 1 (128 threads, 105 KB, ~190 registers) is the default: such a CTA fits on an SM NEXT TO one CTA of the
+// GEMM core (gemm128.cuh: 128 threads, 92 KB), so the substitution latency of one stream group hides behind the
+// DMMA work of another instead of idling an SM; GROUPS = 2 (256 threads) does not.
+// grid = (ceil((nt-k-1)/(2*GROUPS)), nmat), block = 128*GROUPS, dynamic smem TRSM_COL_SMEM(GROUPS).
+#define TRSM_COL_SMEM(G) (((1 + 2 * (G)) * NB * LDT + NB) * sizeof(double))
+template <int GROUPS>
+__global__ void __launch_bounds__(128 * GROUPS) trsm_col_kernel(double* __restrict__ W, const int* __restrict__ ids,
+                                                                int Np, int k, int k0) {
     GPRN_TRACE_SCOPE(TK_TRSM);
+    constexpr int NTHR = 128 * GROUPS, VLD = (GROUPS == 2) ? LDV4 : LDV2;
     extern __shared__ double smem[];
     double* Bs = smem;                 // L_kk' operand, then L_kk
-    double* As = smem + NB * LDT;      // four row-tile operands; then V (substitution vectors, stride 257)
+    double* As = smem + NB * LDT;      // 2*GROUPS row-tile operands; then V (substitution vectors, stride VLD)
     double* V = As;
-    double* rd = smem + 5 * NB * LDT;
+    double* rd = smem + (1 + 2 * GROUPS) * NB * LDT;
     const int nt = Np / NB;
     const int id = ids[blockIdx.y];
     double* Wm = W + (size_t)id * Np * Np;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int grp = warp >> 2, w4 = warp & 3, wm = w4 >> 1, wn = w4 & 1, tid4 = tid & 127;
     const int r = lane >> 2, c = lane & 3;
-    const int ibase = k + 1 + 4 * blockIdx.x;
+    const int ibase = k + 1 + 2 * GROUPS * blockIdx.x;
     const int ia = ibase + 2 * grp, ib = ia + 1;
     const bool hasa = ia < nt, hasb = ib < nt;
     double acca[4][4][2], accb[4][4][2];
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(256) trsm_col_kernel(double* __restrict__ W, c
     double* Aa = As + (2 * grp) * NB * LDT;
     double* Ab = Aa + NB * LDT;
     for (int kp = k0; kp < k; kp++) {
-        load_tile<false>(Bs, Wm + (size_t)(k * NB) * Np + kp * NB, Np, tid, 256);
+        load_tile<false>(Bs, Wm + (size_t)(k * NB) * Np + kp * NB, Np, tid, NTHR);
         if (hasa) load_tile<false>(Aa, Wm + (size_t)(ia * NB) * Np + kp * NB, Np, tid4, 128);
         if (hasb) load_tile<false>(Ab, Wm + (size_t)(ib * NB) * Np + kp * NB, Np, tid4, 128);
         __syncthreads();
@@ -266,32 +270,32 @@ __global__ void __launch_bounds__(256) trsm_col_kernel(double* __restrict__ W, c
         for (int b = 0; b < 4; b++) {
             const int m = wm * 32 + a * 8 + r, n = wn * 32 + b * 8 + 2 * c;
             if (hasa) {
-                V[n * TRSM4_LDV + (2 * grp) * NB + m] = acca[a][b][0];
-                V[(n + 1) * TRSM4_LDV + (2 * grp) * NB + m] = acca[a][b][1];
+                V[n * VLD + (2 * grp) * NB + m] = acca[a][b][0];
+                V[(n + 1) * VLD + (2 * grp) * NB + m] = acca[a][b][1];
             }
             if (hasb) {
-                V[n * TRSM4_LDV + (2 * grp + 1) * NB + m] = accb[a][b][0];
-                V[(n + 1) * TRSM4_LDV + (2 * grp + 1) * NB + m] = accb[a][b][1];
+                V[n * VLD + (2 * grp + 1) * NB + m] = accb[a][b][0];
+                V[(n + 1) * VLD + (2 * grp + 1) * NB + m] = accb[a][b][1];
             }
         }
-    load_tile<false>(Bs, Wm + (size_t)(k * NB) * Np + k * NB, Np, tid, 256);
+    load_tile<false>(Bs, Wm + (size_t)(k * NB) * Np + k * NB, Np, tid, NTHR);
     __syncthreads();
     if (tid < NB) rd[tid] = 1.0 / Bs[tid * LDT + tid];
     __syncthreads();
-    if (ibase + (warp >> 1) < nt) subst_lower_mma<4>(Bs, LDT, rd, V, TRSM4_LDV, (warp >> 1) * NB + (warp & 1) * 32);
+    if (ibase + (warp >> 1) < nt) subst_lower_mma<4>(Bs, LDT, rd, V, VLD, (warp >> 1) * NB + (warp & 1) * 32);
     __syncthreads();
     if (hasa) {
         double* dst = Wm + (size_t)(ia * NB) * Np + k * NB;
         for (int e = tid4; e < NB * NB; e += 128) {
             int m = e >> 6, n = e & 63;
-            dst[(size_t)m * Np + n] = V[n * TRSM4_LDV + (2 * grp) * NB + m];
+            dst[(size_t)m * Np + n] = V[n * VLD + (2 * grp) * NB + m];
         }
     }
     if (hasb) {
         double* dst = Wm + (size_t)(ib * NB) * Np + k * NB;
         for (int e = tid4; e < NB * NB; e += 128) {
             int m = e >> 6, n = e & 63;
-            dst[(size_t)m * Np + n] = V[n * TRSM4_LDV + (2 * grp + 1) * NB + m];
+            dst[(size_t)m * Np + n] = V[n * VLD + (2 * grp + 1) * NB + m];
         }
     }
 }

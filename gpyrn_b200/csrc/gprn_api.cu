@@ -160,7 +160,8 @@ static int set_kernel_attrs() {
     if (g_attr_done) return 0;
     CU(cudaFuncSetAttribute(panel_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
     CU(cudaFuncSetAttribute(potrf_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_COL_SMEM));
-    CU(cudaFuncSetAttribute(trsm_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_COL_SMEM));
+    CU(cudaFuncSetAttribute(trsm_col_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_COL_SMEM(1)));
+    CU(cudaFuncSetAttribute(trsm_col_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_COL_SMEM(2)));
     CU(cudaFuncSetAttribute(syrk_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(trtri_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
     CU(cudaFuncSetAttribute(trtri_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_DIAG_SMEM));
@@ -369,7 +370,11 @@ static int factor_batch(gprn_handle* h, double* W, const int* d_ids, int nmat, d
                 launch_hi(potrf_col_kernel, dim3(nmat), dim3(256), POTRF_COL_SMEM, st, W, d_ids, Np, k, k0, logdet, mstatus);
                 LAUNCH_CHECK(h);
                 if (n > 0) {
-                    launch_hi(trsm_col_kernel, dim3((n + 3) / 4, nmat), dim3(256), TRSM_COL_SMEM, st, W, d_ids, Np, k, k0);
+                    static const int trsm_groups = getenv("GPRN_TRSM_GROUPS") ? atoi(getenv("GPRN_TRSM_GROUPS")) : 1;
+                    if (trsm_groups == 2)
+                        launch_hi(trsm_col_kernel<2>, dim3((n + 3) / 4, nmat), dim3(256), TRSM_COL_SMEM(2), st, W, d_ids, Np, k, k0);
+                    else
+                        launch_hi(trsm_col_kernel<1>, dim3((n + 1) / 2, nmat), dim3(128), TRSM_COL_SMEM(1), st, W, d_ids, Np, k, k0);
                     LAUNCH_CHECK(h);
                 }
             }
