@@ -29,26 +29,60 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
                  : "d"(a), "d"(b));
 }
 
+// Asynchronous global -> shared copies (LDGSTS): 16 bytes bypassing L1, or 8 bytes (transposing scatters).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
 // Load a 64x64 tile from global memory (row-major, leading dimension ld) into shared memory
 // dst[64][LDT].  TRANS: dst[m][k] = src[k*ld + m].  `scale` (optional, length 64) multiplies along
 // the k index of dst (used for the D-weighted cross term).  All `nthreads` threads of the CTA call.
-template <bool TRANS>
+// Without `scale` the copy is issued as cp.async (every element of the tile is in flight at once: one memory round
+// trip per tile instead of one per unrolled batch of register loads) and, with WAIT, completed for the calling thread
+// before returning; the caller's __syncthreads() then publishes it.  WAIT = false: the caller batches several tiles
+// and ends with cp_async_commit(); cp_async_wait<0>().
+template <bool TRANS, bool WAIT = true>
 __device__ __forceinline__ void load_tile(double* __restrict__ dst, const double* __restrict__ src, size_t ld,
                                           int tid, int nthreads, const double* __restrict__ scale = nullptr) {
+    if (scale == nullptr) {
+        if (!TRANS) {
+            for (int e = tid; e < NB * (NB / 2); e += nthreads) {
+                int r = e >> 5, c2 = e & 31;
+                cp_async16(dst + r * LDT + 2 * c2, src + (size_t)r * ld + 2 * c2);
+            }
+        } else {
+            for (int e = tid; e < NB * NB; e += nthreads) {
+                int k = e >> 6, m = e & 63;          // coalesced along m in global memory
+                cp_async8(dst + m * LDT + k, src + (size_t)k * ld + m);
+            }
+        }
+        if (WAIT) {
+            cp_async_commit();
+            cp_async_wait<0>();
+        }
+        return;
+    }
     if (!TRANS) {
         // 64 rows x 32 double2
         for (int e = tid; e < NB * (NB / 2); e += nthreads) {
             int r = e >> 5, c2 = e & 31;
             double2 v = *reinterpret_cast<const double2*>(src + (size_t)r * ld + 2 * c2);
-            if (scale) { v.x *= scale[2 * c2]; v.y *= scale[2 * c2 + 1]; }
+            v.x *= scale[2 * c2];
+            v.y *= scale[2 * c2 + 1];
             *reinterpret_cast<double2*>(dst + r * LDT + 2 * c2) = v;
         }
     } else {
         for (int e = tid; e < NB * NB; e += nthreads) {
             int k = e >> 6, m = e & 63;          // coalesced along m in global memory
-            double v = src[(size_t)k * ld + m];
-            if (scale) v *= scale[k];
-            dst[m * LDT + k] = v;
+            dst[m * LDT + k] = src[(size_t)k * ld + m] * scale[k];
         }
     }
 }

@@ -88,8 +88,10 @@ __global__ void __launch_bounds__(256) panel_col_kernel(double* __restrict__ W, 
             }
         }
     for (int kp = k0; kp < k; kp++) {
-        load_tile<false>(Bs, Wm + (size_t)(k * NB) * Np + kp * NB, Np, tid, 256);
-        if (has) load_tile<false>(grp ? As1 : As0, Wm + (size_t)(i_own * NB) * Np + kp * NB, Np, tid4, 128);
+        load_tile<false, false>(Bs, Wm + (size_t)(k * NB) * Np + kp * NB, Np, tid, 256);
+        if (has) load_tile<false, false>(grp ? As1 : As0, Wm + (size_t)(i_own * NB) * Np + kp * NB, Np, tid4, 128);
+        cp_async_commit();
+        cp_async_wait<0>();
         __syncthreads();
         if (grp == 0) mma_tile<true>(accd, Bs, Bs, wm, wn, lane);
         if (has) mma_tile<true>(accr, grp ? As1 : As0, Bs, wm, wn, lane);
@@ -256,9 +258,11 @@ __global__ void __launch_bounds__(128 * GROUPS) trsm_col_kernel(double* __restri
     double* Aa = As + (2 * grp) * NB * LDT;
     double* Ab = Aa + NB * LDT;
     for (int kp = k0; kp < k; kp++) {
-        load_tile<false>(Bs, Wm + (size_t)(k * NB) * Np + kp * NB, Np, tid, NTHR);
-        if (hasa) load_tile<false>(Aa, Wm + (size_t)(ia * NB) * Np + kp * NB, Np, tid4, 128);
-        if (hasb) load_tile<false>(Ab, Wm + (size_t)(ib * NB) * Np + kp * NB, Np, tid4, 128);
+        load_tile<false, false>(Bs, Wm + (size_t)(k * NB) * Np + kp * NB, Np, tid, NTHR);
+        if (hasa) load_tile<false, false>(Aa, Wm + (size_t)(ia * NB) * Np + kp * NB, Np, tid4, 128);
+        if (hasb) load_tile<false, false>(Ab, Wm + (size_t)(ib * NB) * Np + kp * NB, Np, tid4, 128);
+        cp_async_commit();
+        cp_async_wait<0>();
         __syncthreads();
         if (hasa) mma_tile<true>(acca, Aa, Bs, wm, wn, lane);
         if (hasb) mma_tile<true>(accb, Ab, Bs, wm, wn, lane);
@@ -574,8 +578,10 @@ __global__ void __launch_bounds__(128) trtri_inblock_kernel(double* __restrict__
                 for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
         }
         for (int k = kstart; k < i; k++) {
-            load_tile<false>(As, Wm + (size_t)(i * NB) * Np + k * NB, Np, tid, 128);
-            load_tile<true>(Bs, Xm + (size_t)(k * NB) * Np + j * NB, Np, tid, 128);
+            load_tile<false, false>(As, Wm + (size_t)(i * NB) * Np + k * NB, Np, tid, 128);
+            load_tile<true, false>(Bs, Xm + (size_t)(k * NB) * Np + j * NB, Np, tid, 128);
+            cp_async_commit();
+            cp_async_wait<0>();
             __syncthreads();
             mma_tile<true>(acc, As, Bs, wm, wn, lane);
             __syncthreads();

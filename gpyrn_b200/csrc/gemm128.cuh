@@ -51,14 +51,6 @@ namespace gprn {
 #define G_B_STAGE_NN (G_BK * G_LDB_NN)
 #define GEMM128_SMEM (G_STAGES * (G_A_STAGE + G_B_STAGE_NT) * sizeof(double))   // NT is the larger one
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
 // Issue the loads of one k-slab (16 deep) into one pipeline stage.
 template <bool B_KMAJOR>
 __device__ __forceinline__ void gemm128_load_stage(double* As, double* Bs, const double* __restrict__ A, size_t lda,

@@ -116,8 +116,10 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
                 const bool diag = (s == 0 && grp == 0);
                 SMALL_PH(2);
                 for (int kp = 0; kp < k; kp++) {
-                    load_tile<false>(Bs, small_tile(sc, k, kp), NB, tid, 256);
-                    if (have && !diag) load_tile<false>(grp ? As1 : As0, small_tile(sc, it, kp), NB, tid4, 128);
+                    load_tile<false, false>(Bs, small_tile(sc, k, kp), NB, tid, 256);
+                    if (have && !diag) load_tile<false, false>(grp ? As1 : As0, small_tile(sc, it, kp), NB, tid4, 128);
+                    cp_async_commit();
+                    cp_async_wait<0>();
                     __syncthreads();
                     if (have) mma_tile<true>(acc, diag ? Bs : (grp ? As1 : As0), Bs, wm, wn, lane);
                     __syncthreads();
@@ -205,9 +207,11 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
 #pragma unroll
                     for (int y = 0; y < 4; y++) acc[x][y][0] = acc[x][y][1] = 0.0;
                 for (int k = j0; k < i; k++) {
-                    load_tile<false>(Bs, small_tile(sc, i, k), NB, tid, 256);                       // L_ik (shared A operand)
+                    load_tile<false, false>(Bs, small_tile(sc, i, k), NB, tid, 256);                // L_ik (shared A operand)
                     const bool part = (j < i) && (k >= j);
-                    if (part) load_tile<true>(grp ? As1 : As0, small_tile(sc, k, j), NB, tid4, 128);   // X_kj^T
+                    if (part) load_tile<true, false>(grp ? As1 : As0, small_tile(sc, k, j), NB, tid4, 128);   // X_kj^T
+                    cp_async_commit();
+                    cp_async_wait<0>();
                     __syncthreads();
                     if (part) mma_tile<true>(acc, Bs, grp ? As1 : As0, wm, wn, lane);
                     __syncthreads();
