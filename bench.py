@@ -218,12 +218,19 @@ def run_ours(args, w):
     theta = workloads.perturbed_sets(th0, pool_B, w["seed"])
     blocks = None
     try:
-        rec = json.load(open(os.path.join(ROOT, "profiles", f"iterations_{args.workload}.json")))["iterations"]
+        recd = json.load(open(os.path.join(ROOT, "profiles", f"iterations_{args.workload}.json")))
+        rec = recd["iterations"]
         if len(rec) >= pool_B and not args.no_balance:
-            blocks = D.balanced_assignment(rec[:pool_B], pool_B // B_local)
-            # blocks have (nearly) equal summed cost; order them by their longest evaluation so that block 0 -- the
-            # N = 1 workload -- is the one with the shortest straggler tail, and larger N add the longer-tailed ones
-            blocks.sort(key=lambda b: (max(rec[i] for i in b), sum(rec[i] for i in b)))
+            # lock-step cost model (time of one iteration with 1..k active sets, measured): a block that ends in a
+            # long single-set tail costs more than its iteration sum says
+            st = recd.get("lockstep_ms") if B_local == len(recd.get("lockstep_ms", [])) else None
+            blocks = D.balanced_assignment(rec[:pool_B], pool_B // B_local, step_times=st)
+            # blocks have (nearly) equal cost; order them by the distance of their cost from the mean so that block 0
+            # -- the N = 1 workload -- is the most typical one and small N stay representative of the pool
+            cost = [D.lockstep_cost([rec[i] for i in b], st) if st else float(sum(rec[i] for i in b)) for b in blocks]
+            mean = sum(cost) / len(cost)
+            blocks = [b for _, _, b in sorted(zip([abs(c - mean) for c in cost], range(len(blocks)), blocks),
+                                              key=lambda x: (x[0], x[1]))]
     except Exception:
         blocks = None
     if blocks is not None:
@@ -328,7 +335,7 @@ def run_ours(args, w):
                "config": {"workload": w["name"], "N": N, "p": p, "q": q, "sets_per_gpu": B_local, "global_sets": B,
                           "mean_iterations": iters_step / B, "elbo_iterations_per_sec": iters_step * args.steps / (ms_tot * 1e-3),
                           "not_converged_or_failed": int(bad),
-                          "sharding": ("equal-cost blocks from recorded iteration counts (profiles/iterations_%s.json); rank r always evaluates block r" % args.workload)
+                          "sharding": ("equal-cost blocks from recorded iteration counts and the measured lock-step iteration times (profiles/iterations_%s.json); rank r always evaluates block r" % args.workload)
                           if blocks is not None else ("round-robin" if (world == 1 or args.no_balance) else
                                                       "round-robin, re-dealt by warm-up iteration counts (equal sets per rank)"),
                           "l2": "256 MiB flush between steps; per-step working set (K, L, L^-1 per matrix) >> 126 MB L2",

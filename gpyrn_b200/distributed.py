@@ -25,18 +25,52 @@ def shard_indices(B, world_size, rank, mode="strided"):
     raise ValueError(f"unknown shard mode {mode!r}")
 
 
-def balanced_assignment(costs, world_size):
-    """Equal-count partition of the sets over ranks that evens out the summed cost (iteration counts of a
-    previous pass are a good predictor: the fixed point a set converges to moves little between passes).
+def lockstep_cost(iters, step_times):
+    """Cost of evaluating a block of sets in lock-step (one batched call): while n sets are still active an iteration
+    takes ``step_times[n-1]``; the sets drop out one by one as they converge."""
+    it = np.sort(np.asarray(iters, dtype=float))
+    n = it.size
+    cost, prev = 0.0, 0.0
+    for k in range(n):                       # n - k sets are active between it[k-1] and it[k]
+        cost += (it[k] - prev) * step_times[min(n - k, len(step_times)) - 1]
+        prev = it[k]
+    return cost
 
-    Sets are sorted by cost and dealt in serpentine order, so every rank receives the same number of sets
-    (+-1) and the per-rank cost sums differ by at most one cost gap per round.  Returns a list of index arrays."""
+
+def balanced_assignment(costs, world_size, step_times=None):
+    """Equal-count partition of the sets over ranks that evens out the cost (iteration counts of a previous pass
+    are a good predictor: the fixed point a set converges to moves little between passes).
+
+    Sets are sorted by cost and dealt in serpentine order, so every rank receives the same number of sets (+-1)
+    and the per-rank cost sums differ by at most one cost gap per round.  With ``step_times`` (measured time of one
+    lock-step iteration with 1, 2, ... active sets) the blocks are then refined by pairwise swaps that lower the
+    largest ``lockstep_cost`` -- a rank whose block ends in a long single-set tail pays more per iteration than one
+    whose sets converge together.  Deterministic.  Returns a list of index arrays."""
     costs = np.asarray(costs, dtype=float)
     order = np.argsort(-costs, kind="stable")
     out = [[] for _ in range(world_size)]
     for pos, i in enumerate(order):
         rnd, k = divmod(pos, world_size)
         out[k if rnd % 2 == 0 else world_size - 1 - k].append(int(i))
+    if step_times is not None and world_size > 1:
+        cost = lambda blk: lockstep_cost(costs[blk], step_times)
+        for _ in range(200):
+            bc = [cost(b) for b in out]
+            worst = int(np.argmax(bc))
+            best = None
+            for other in range(world_size):
+                if other == worst:
+                    continue
+                for ia, a in enumerate(out[worst]):
+                    for ib, b in enumerate(out[other]):
+                        na = out[worst][:ia] + [b] + out[worst][ia + 1:]
+                        nb = out[other][:ib] + [a] + out[other][ib + 1:]
+                        m = max(cost(na), cost(nb))
+                        if m < bc[worst] - 1e-9 and (best is None or m < best[0]):
+                            best = (m, other, na, nb)
+            if best is None:
+                break
+            out[worst], out[best[1]] = best[2], best[3]
     return [np.array(sorted(o), dtype=np.int64) for o in out]
 
 

@@ -38,6 +38,26 @@ def test_balanced_assignment():
             assert max(sums) - min(sums) <= max(naive) - min(naive) + costs.max()
 
 
+def test_balanced_assignment_with_lockstep_cost_model():
+    """Blocks evaluated in lock-step: a block pays step_times[n-1] per iteration while n of its sets are active.
+    The refinement must keep the partition valid and not increase the largest modelled block cost."""
+    st = [24.65, 40.15, 56.8, 74.25]
+    assert D.lockstep_cost([10, 10, 10, 10], st) == pytest.approx(10 * st[3])
+    assert D.lockstep_cost([5, 20], st) == pytest.approx(5 * st[1] + 15 * st[0])
+    rng = np.random.default_rng(1)
+    for trial in range(5):
+        costs = rng.integers(30, 100, 32)
+        base = D.balanced_assignment(costs, 8)
+        ref = D.balanced_assignment(costs, 8, step_times=st)
+        assert sorted(np.concatenate(ref).tolist()) == list(range(32)) and all(len(b) == 4 for b in ref)
+        worst = lambda blocks: max(D.lockstep_cost(costs[b], st) for b in blocks)
+        assert worst(ref) <= worst(base) + 1e-9
+    rec = [44, 54, 40, 55, 42, 60, 40, 62, 44, 43, 53, 58, 38, 51, 41, 34, 53, 50, 67, 77, 53, 69, 79, 40, 67, 42, 71,
+           63, 94, 68, 53, 73]                      # profiles/iterations_c4.json
+    c = [D.lockstep_cost(np.array(rec)[b], st) for b in D.balanced_assignment(rec, 8, step_times=st)]
+    assert max(c) / min(c) < 1.03                   # 1.12 with the iteration sums alone
+
+
 def test_gather_single_process():
     idx = np.array([0, 2, 4])
     out = D.gather_results(idx, {"elbo": np.array([1.0, 2.0, 3.0])}, 5)
