@@ -1,13 +1,18 @@
-// factor.cuh -- batched blocked Cholesky and triangular inverse (FP64 compute bound).
+// factor.cuh -- batched blocked Cholesky and triangular inverse (FP64 compute bound), batched over an arbitrary
+// list of matrices (blockIdx.y).
 //
-// Right-looking blocked Cholesky with 64x64 tiles, one launch per role and block step, batched over
-// an arbitrary list of matrices (blockIdx.y):
-//     potrf_diag   : L_kk = chol(A_kk)                 (shared memory, one CTA per matrix)
-//     trsm_panel   : L_ik = A_ik L_kk^-T               (forward substitution, one row per thread)
-//     syrk_update  : A_ij -= L_ik L_jk^T               (DMMA m8n8k4 tiles, the only dense contraction)
-// and the inverse factor X = L^-1 by block rows:
-//     trtri_diag   : X_ii = L_ii^-1
-//     trtri_row    : X_ij = -L_ii^-1 * sum_{k=j}^{i-1} L_ik X_kj     (DMMA accumulate + substitution)
+// Cholesky, 64x64 tiles, panels of 4 tile columns (left-looking inside a panel, right-looking between panels):
+//     panel_col              : one tile column in ONE launch -- in-panel update, potrf64 of the diagonal tile
+//                              (redundantly per CTA), forward substitution of two row tiles       [latency-bound regime]
+//     potrf_col + trsm_col   : the same step as two launches, diagonal tile factored once          [SM-bound regime]
+//     syrk_update            : trailing update with 64x64 DMMA tiles (sizes that are not 256-aligned)
+//     syrk_outer             : trailing update on the GEMM core of gemm128.cuh (two-level path, Np % 256 == 0)
+// Inverse factor X = L^-1 by block rows:
+//     trtri_diag             : X_ii = L_ii^-1
+//     trtri_row              : X_ij = -L_ii^-1 * sum_{k=j}^{i-1} L_ik X_kj   (64-tile path)
+//     trtri_outer + trtri_inblock : the same sum split into a GEMM-core part (rows above the 256-row block) and an
+//                              in-block sweep with substitution (two-level path)
+// plus the triangular matrix-vector passes (trmv_lower, trmv_upper_norm).
 // Replaces jnp.linalg.cholesky (gpyrn/meanfield.py:88), np.linalg.solve (:771,:850),
 // cho_solve (:1032-1051) and scipy cho_factor/cho_solve (gpyrn/_gp.py:126-135).
 #pragma once
