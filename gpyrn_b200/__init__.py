@@ -9,7 +9,7 @@ __version__ = '0.1.0'
 from .meanfunc import Constant, Linear
 from .covfunc import SquaredExponential, QuasiPeriodic
 from .meanfield import inference
-from . import covfunc, meanfunc, meanfield, distributed
+from . import covfunc, meanfunc, meanfield, distributed, datasets
 
 __all__ = ['Constant', 'Linear', 'SquaredExponential', 'QuasiPeriodic', 'inference',
            'covfunc', 'meanfunc', 'meanfield', 'distributed']

@@ -215,3 +215,22 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(root, f)).read()
                 assert "oracle" not in src, f"{f} mentions the oracle"
+
+
+def test_observation_table_loader(tmp_path):
+    """loader for tables in the format of the reference's bundled Solar_observations.txt."""
+    from gpyrn_b200 import datasets
+    f = tmp_path / "obs.txt"
+    f.write_text("BJD\tRV\tRVerr\tBIS\tBISerr\tConstrast\tContrasterr\n"
+                 "3.0\t1.5\t0.1\t-8.0\t0.2\t40.0\t0.5\n"
+                 "1.0\t2.5\t0.3\t-9.0\t0.4\t41.0\t0.6\n")
+    tab = datasets.load_table(str(f))
+    assert list(tab) == ["BJD", "RV", "RVerr", "BIS", "BISerr", "Constrast", "Contrasterr"]
+    t, series = datasets.load_observations(str(f), ("RV", "BIS", "Constrast"))
+    assert np.allclose(t, [1.0, 3.0]) and len(series) == 6
+    assert np.allclose(series[0], [2.5, 1.5]) and np.allclose(series[1], [0.3, 0.1])
+    assert np.allclose(series[4], [41.0, 40.0]) and np.allclose(series[5], [0.6, 0.5])
+    g = gpyrn_b200.inference(1, t, *series)            # host-side construction only
+    assert g.p == 3 and g.N == 2
+    with pytest.raises(KeyError):
+        datasets.load_observations(str(f), ("FWHM",))
