@@ -43,47 +43,28 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // Load a 64x64 tile from global memory (row-major, leading dimension ld) into shared memory
-// dst[64][LDT].  TRANS: dst[m][k] = src[k*ld + m].  `scale` (optional, length 64) multiplies along
-// the k index of dst (used for the D-weighted cross term).  All `nthreads` threads of the CTA call.
-// Without `scale` the copy is issued as cp.async (every element of the tile is in flight at once: one memory round
-// trip per tile instead of one per unrolled batch of register loads) and, with WAIT, completed for the calling thread
-// before returning; the caller's __syncthreads() then publishes it.  WAIT = false: the caller batches several tiles
-// and ends with cp_async_commit(); cp_async_wait<0>().
+// dst[64][LDT].  TRANS: dst[m][k] = src[k*ld + m].  All `nthreads` threads of the CTA call.
+// The copy is issued as cp.async (every element of the tile is in flight at once: one memory round trip per tile
+// instead of one per unrolled batch of register loads) and, with WAIT, completed for the calling thread before
+// returning; the caller's __syncthreads() then publishes it.  WAIT = false: the caller batches several tiles and
+// ends with cp_async_commit(); cp_async_wait<0>().
 template <bool TRANS, bool WAIT = true>
 __device__ __forceinline__ void load_tile(double* __restrict__ dst, const double* __restrict__ src, size_t ld,
-                                          int tid, int nthreads, const double* __restrict__ scale = nullptr) {
-    if (scale == nullptr) {
-        if (!TRANS) {
-            for (int e = tid; e < NB * (NB / 2); e += nthreads) {
-                int r = e >> 5, c2 = e & 31;
-                cp_async16(dst + r * LDT + 2 * c2, src + (size_t)r * ld + 2 * c2);
-            }
-        } else {
-            for (int e = tid; e < NB * NB; e += nthreads) {
-                int k = e >> 6, m = e & 63;          // coalesced along m in global memory
-                cp_async8(dst + m * LDT + k, src + (size_t)k * ld + m);
-            }
-        }
-        if (WAIT) {
-            cp_async_commit();
-            cp_async_wait<0>();
-        }
-        return;
-    }
+                                          int tid, int nthreads) {
     if (!TRANS) {
-        // 64 rows x 32 double2
         for (int e = tid; e < NB * (NB / 2); e += nthreads) {
             int r = e >> 5, c2 = e & 31;
-            double2 v = *reinterpret_cast<const double2*>(src + (size_t)r * ld + 2 * c2);
-            v.x *= scale[2 * c2];
-            v.y *= scale[2 * c2 + 1];
-            *reinterpret_cast<double2*>(dst + r * LDT + 2 * c2) = v;
+            cp_async16(dst + r * LDT + 2 * c2, src + (size_t)r * ld + 2 * c2);
         }
     } else {
         for (int e = tid; e < NB * NB; e += nthreads) {
             int k = e >> 6, m = e & 63;          // coalesced along m in global memory
-            dst[m * LDT + k] = src[(size_t)k * ld + m] * scale[k];
+            cp_async8(dst + m * LDT + k, src + (size_t)k * ld + m);
         }
+    }
+    if (WAIT) {
+        cp_async_commit();
+        cp_async_wait<0>();
     }
 }
 
@@ -105,6 +86,29 @@ __device__ __forceinline__ void mma_tile(double (&acc)[4][4][2], const double* _
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) b[j] = bp[j * 8 * LDT + k0];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j], a[i], b[j]);
+    }
+}
+
+// acc += As * diag(sc) * Bs^T: as mma_tile, with the B fragment multiplied by sc[k] (64 doubles in shared memory) as it
+// is loaded -- the same rounding as scaling the tile when it is stored, without a register round trip at load time.
+__device__ __forceinline__ void mma_tile_scaled(double (&acc)[4][4][2], const double* __restrict__ As,
+                                                const double* __restrict__ Bs, const double* __restrict__ sc, int wm,
+                                                int wn, int lane) {
+    const int r = lane >> 2, c = lane & 3;
+    const double* ap = As + (wm * 32 + r) * LDT + c;
+    const double* bp = Bs + (wn * 32 + r) * LDT + c;
+#pragma unroll 4
+    for (int k0 = 0; k0 < NB; k0 += 4) {
+        double a[4], b[4];
+        const double s = sc[k0 + c];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = ap[i * 8 * LDT + k0];
+#pragma unroll
+        for (int j = 0; j < 4; j++) b[j] = bp[j * 8 * LDT + k0] * s;
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll

@@ -246,11 +246,15 @@ __global__ void __launch_bounds__(128) cross_frob_kernel(ElboCtx c, const double
 #pragma unroll
         for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
     const int kmax = min(ta, tb);
+    __shared__ double sc[NB];
     for (int kt = 0; kt <= kmax; kt++) {
-        load_tile<false>(As, xk + (size_t)(ta * NB) * Np + kt * NB, Np, tid, 128);
-        load_tile<false>(Bs, xa + (size_t)(tb * NB) * Np + kt * NB, Np, tid, 128, Dk + kt * NB);
+        load_tile<false, false>(As, xk + (size_t)(ta * NB) * Np + kt * NB, Np, tid, 128);
+        load_tile<false, false>(Bs, xa + (size_t)(tb * NB) * Np + kt * NB, Np, tid, 128);
+        if (tid < NB) sc[tid] = Dk[kt * NB + tid];
+        cp_async_commit();
+        cp_async_wait<0>();
         __syncthreads();
-        mma_tile<false>(acc, As, Bs, wm, wn, lane);
+        mma_tile_scaled(acc, As, Bs, sc, wm, wn, lane);
         __syncthreads();
     }
     // rows/cols >= N belong to the identity padding and must not be counted
