@@ -234,3 +234,22 @@ def test_observation_table_loader(tmp_path):
     assert g.p == 3 and g.N == 2
     with pytest.raises(KeyError):
         datasets.load_observations(str(f), ("FWHM",))
+
+
+def test_trace_analysis_tool_on_synthetic_records(tmp_path, capsys):
+    """tools/trace_run.py --analyse: SM-time attribution of a per-CTA trace (no GPU needed for the analysis)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("trace_run", os.path.join(ROOT, "tools", "trace_run.py"))
+    tr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tr)
+    dt = np.dtype([("t0", "<u8"), ("t1", "<u8"), ("kid", "<i4"), ("smid", "<i4")])
+    rec = np.zeros(4, dtype=dt)
+    rec[0] = (1000, 101000, 5, 0)        # syrk_outer on SM 0 for 100 us
+    rec[1] = (1000, 51000, 3, 1)         # trsm_col on SM 1 for 50 us
+    rec[2] = (51000, 101000, 8, 1)       # trtri_outer on SM 1 for 50 us
+    rec[3] = (1000, 101000, 9, 0)        # trtri_inblock co-resident with the GEMM CTA on SM 0
+    tr.analyse(rec, nsm=2)
+    out = capsys.readouterr().out
+    assert "syrk_outer" in out and "trsm_col" in out
+    gemm = float(re.search(r"GEMM-class CTA .* resident: ([0-9.]+) %", out).group(1))
+    assert 70.0 < gemm < 80.0            # SM 0 always, SM 1 half of the time
