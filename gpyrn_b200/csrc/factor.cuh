@@ -152,8 +152,7 @@ __global__ void __launch_bounds__(256) panel_col_kernel(double* __restrict__ W, 
 // The same panel step as two launches (default): potrf_col_kernel factors the diagonal tile once per matrix,
 // trsm_col_kernel then solves FOUR row tiles per CTA (all 256 threads carry a substitution vector).  Compared with
 // panel_col_kernel this drops the redundant per-CTA potrf64 and halves the CTA count, so a panel step holds
-// roughly a third of the SM time -- SMs that the 128x128 GEMM launches of the other stream groups can use
-// (a GEMM CTA needs a whole register file, so it never shares an SM with a panel CTA).  Same arithmetic, same
+// roughly a third of the SM time -- SMs that the GEMM launches of the other stream groups can use.  Same arithmetic, same
 // summation order as panel_col_kernel: the factors are bit-identical.
 // potrf_col_kernel: grid = (nmat), block = 256, dynamic smem POTRF_COL_SMEM.
 #define POTRF_COL_SMEM ((NB * LDT + 4 * NB) * sizeof(double))
@@ -426,7 +425,7 @@ __global__ void __launch_bounds__(128) trtri_row_kernel(double* __restrict__ X, 
 // ------------------------------------------------------------------------------------------------
 // Large-N path (Np a multiple of 256): two-level blocking.  Panels of 256 columns are factored with the
 // 64-tile kernels above (syrk restricted to the panel's own columns); the trailing matrix is then updated
-// once per panel with 128x128 tiles and a K = 256 deep DMMA product (gemm128.cuh).
+// with 128x128 tiles (two 64x128 CTAs each) and K = 256 / 512 deep DMMA products (gemm128.cuh).
 // ------------------------------------------------------------------------------------------------
 #define OUTER_KB 256
 
@@ -479,7 +478,7 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) syrk_outer_kernel(double* _
 }
 
 // Inverse, block row of 256 rows starting at R0: X[rows, 0:R0] = - L[rows, n0:R0] X[n0:R0, cols] (the part of
-// the row-sweep sum that lies above the block), 128x128 tiles.  X must hold zeros in its upper tiles.
+// the row-sweep sum that lies above the block), G_BM x 128 tiles.  X must hold zeros in its upper tiles.
 // The K range of a tile, R0 - n0, shrinks with its column, which leaves most SMs idle behind the few long tiles
 // when few matrices are in flight.  The host can therefore cut the range into chunks of kc (>= TRTRI_KC): chunk 0
 // writes to X as before, chunk s >= 1 to the partial buffer Gp[id][s-1] (256 x Np strip, same row/column indexing);

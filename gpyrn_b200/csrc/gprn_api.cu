@@ -925,7 +925,7 @@ extern "C" int gprn_predict(gprn_handle* h, const double* hyper, const double* m
     if (solve_batch(h, ck.X, ck.d_ids_all, M, c.vv, c.zv, c.uv, c.gv, ck.vec_elems, st)) return 1;   // uv = alpha
     // test points in chunks
     const int TC = 4096;
-    const bool big = (Np % G_BN == 0) && Np >= 256;          // 128x128 GEMM core for the variance norms
+    const bool big = (Np % G_BN == 0) && Np >= 256;          // DMMA GEMM core for the variance norms
     const int tunit = big ? G_BM : NB;
     const int Tc = std::min(TC, ((T + tunit - 1) / tunit) * tunit);
     const int nparts = big ? Np / G_BN : 1;
