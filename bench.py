@@ -2,24 +2,36 @@
 """bench.py -- GPRN ELBO evaluations per second on B200 (BASELINE.json metric), with FP64 roofline and
 the reference's CPU path timed beside it.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c2] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c2|c5] [--impl ours|reference]
+                    [--scaling weak|strong] [--pool P] [--slots S]
 
-A *step* is one batched pass of the hot path: every rank evaluates its `sets_per_gpu` hyper-parameter
-sets (each a full ``ELBOcalc`` from mu=var='init' to its own convergence).  Weak scaling: per-GPU work is
-fixed, the sets are independent (no data-path collective); the only exchange is the gather of ELBO values.
+A *step* evaluates a POOL of hyper-parameter sets (each a full ``ELBOcalc`` from mu=var='init' to its own
+convergence) across all ranks and combines the results:
+  * the pool is dealt DYNAMICALLY: every rank keeps `slots` evaluations in flight (continuous batching, gprn_elbo_pool)
+    and takes the next set from one shared counter (an atomic add on the rendezvous store) whenever a slot frees up --
+    no recorded iteration counts, no cost model, natural order of the seed;
+  * the one collective of the path -- an all-reduce of the per-set ELBO / iteration / status arrays, whose per-rank
+    supports are disjoint -- runs INSIDE the timed step (NCCL over NVLink).
+Scaling modes:
+  weak (default, what the driver's 1/2/4/8 series runs): the pool is N replicas of the workload's base pool (the first
+      `pool_per_gpu` sets of the seed), so per-GPU work is identical for every N by construction; replicas of a set
+      land on different GPUs and must agree bit for bit (checked);
+  strong (--scaling strong --pool P): a fixed pool of P natural-order sets whatever N is.
 
 Workloads (BASELINE.json configs / SURVEY.md 8d):
     c4 (default): synth(N=4096, p=4, q=2, Matern52 nodes), theta_b = theta_0 * exp(0.1 z), seed 102
                   -- the configuration the north-star target is quoted on;
     c3: synth(N=256, p=4, q=1, QuasiPeriodic), 8192 sets per GPU, seed 101;
-    c2: synth(N=500, p=4, q=1, QuasiPeriodic), single evaluation per GPU (latency case).
+    c2: synth(N=500, p=4, q=1, QuasiPeriodic), single evaluation per GPU (latency case);
+    c5: synth(N=2048, p=4, q=2, Matern52), lock-step Nelder-Mead sweep (seed 103) + prediction at T = 20000.
 
-JSON line: see README / DESIGN.md "Measurement".  `value` = evaluations/s with hyper-parameters already
-resident in HBM (device-pointer C-ABI entry, CUDA events on the launching stream); `e2e` = the same through
-``inference.ELBO_batch`` with host buffers (H2D of the hyper sets and y - mean, D2H of ELBO/iters/status inside
-the timed region).  `roofline` = algorithmic FP64 flops (M N^3/3 + n_it [(2/3) M + q(q-1)/2] N^3
-per evaluation, with the iteration counts the run actually took) / device time, against the FP64 DMMA peak
-measured on this pool (profiles/fp64_peaks_r01.json; MEASURED_PEAKS.json carries no FP64 entry).
+JSON line: see README / DESIGN.md "Measurement".  `value` = evaluations/s with the pool's hyper-parameters already
+resident in HBM (device-pointer C-ABI entry, CUDA events on the launching stream); `e2e` = the same through the product
+API ``gpyrn_b200.distributed.elbo_pool_sharded`` -> ``inference.ELBO_batch`` with host buffers (H2D of the hyper sets
+and y - mean, D2H of ELBO/iters/status inside the timed region).  `roofline` = algorithmic FP64 flops (SURVEY.md 8d:
+M N^3/3 + n_it [(2/3) M + q(q-1)/2] N^3 per evaluation, with the iteration counts the run actually took) / device time,
+against the FP64 DMMA peak measured on this pool (profiles/fp64_peaks_r01.json; MEASURED_PEAKS.json carries no FP64
+entry).
 """
 import argparse
 import json
@@ -29,7 +41,13 @@ import sys
 import threading
 import time
 
-import numpy as np
+# The reference arm times numpy / scipy on ALL host cores.  torchrun exports OMP_NUM_THREADS=1 to its workers, which
+# would pin OpenBLAS to one thread: fix the thread count before numpy is imported.
+if "reference" in sys.argv:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = os.environ.get("GPRN_CPU_THREADS", str(os.cpu_count() or 1))
+
+import numpy as np  # noqa: E402
 
 # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when NCCL_DEBUG is set in the
 # environment) goes to stderr
@@ -39,12 +57,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    "c4": dict(N=4096, p=4, q=2, node="M52", sets_per_gpu=4, seed=102,
+    "c4": dict(N=4096, p=4, q=2, node="M52", pool_per_gpu=8, seed=102, slots=0,
+               anchor="c4_pool102_set0_4096_4_2_M52_conv",
                name="C4 synth(N=4096,p=4,q=2,Matern52 nodes, SE weights), batched ELBOcalc to convergence"),
-    "c3": dict(N=256, p=4, q=1, node="QP", sets_per_gpu=8192, seed=101,
+    "c3": dict(N=256, p=4, q=1, node="QP", pool_per_gpu=8192, seed=101, slots=0, anchor=None,
                name="C3 synth(N=256,p=4,q=1,QuasiPeriodic node, SE weights), 8192 hyper sets per GPU"),
-    "c2": dict(N=500, p=4, q=1, node="QP", sets_per_gpu=1, seed=101,
+    "c2": dict(N=500, p=4, q=1, node="QP", pool_per_gpu=1, seed=101, slots=0, anchor=None,
                name="C2 synth(N=500,p=4,q=1,QuasiPeriodic node, SE weights), single ELBOcalc"),
+    "c5": dict(N=2048, p=4, q=2, node="M52", pool_per_gpu=8, seed=103, slots=0, anchor=None,
+               name="C5 synth(N=2048,p=4,q=2,Matern52 nodes): lock-step Nelder-Mead sweep + prediction at T=20000"),
 }
 
 
@@ -57,11 +78,13 @@ def fp64_peak():
         return 37.0, "fallback (B200 FP64 nominal 148 SM x 64 FMA x 1.965 GHz)"
 
 
-def algorithmic_flops(N, p, q, iters):
-    """F_eval = M N^3/3 + n_it [(2/3) M + q(q-1)/2] N^3, summed over evaluations."""
+def algorithmic_flops(N, p, q, iters, cross=1.0):
+    """F_eval = M N^3/3 + n_it [(2/3) M + cross * q(q-1)/2] N^3, summed over evaluations.
+    cross = 1: the survey's count of the cross-node trace term; cross = 2/3: what cross_frob_kernel executes (the
+    product of two triangular factors), the cheapest count known."""
     M = q * (p + 1)
     iters = np.asarray(iters, dtype=np.float64)
-    return float(np.sum(M * N ** 3 / 3.0 + iters * ((2.0 / 3.0) * M + q * (q - 1) / 2.0) * N ** 3))
+    return float(np.sum(M * N ** 3 / 3.0 + iters * ((2.0 / 3.0) * M + cross * q * (q - 1) / 2.0) * N ** 3))
 
 
 class ClockSampler(threading.Thread):
@@ -108,98 +131,168 @@ def build_problem(w):
     return a, workloads.theta0(a)
 
 
-def oracle_model(a):
-    """cpu_baseline / reference arm only: the CPU oracle's model container for these inputs."""
-    from oracle import gprn_oracle as orc
-    return orc, orc.Model(a["t"], a["y"], a["yerr"], a["nodes"], a["weights"], None, a["jitters"])
+def pool_of(w, th0, world, scaling, pool):
+    """(hyper [B, H], base pool size).  weak: `world` replicas of the first pool_per_gpu sets of the seed;
+    strong: the first `pool` sets of the seed."""
+    import workloads
+    if scaling == "strong":
+        return workloads.perturbed_sets(th0, pool, w["seed"]), pool
+    base = workloads.perturbed_sets(th0, w["pool_per_gpu"], w["seed"])
+    return np.ascontiguousarray(np.tile(base, (world, 1))), w["pool_per_gpu"]
+
+
+def config_of(args, w, world):
+    """Workload description shared verbatim by both arms (no run-dependent values)."""
+    pool = args.pool if args.scaling == "strong" else w["pool_per_gpu"] * world
+    return {"workload": w["name"], "N": w["N"], "p": w["p"], "q": w["q"], "scaling": args.scaling,
+            "pool_per_gpu": None if args.scaling == "strong" else w["pool_per_gpu"], "global_sets": pool,
+            "seed_data": 1, "seed_hyper": w["seed"]}
 
 
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's numpy/scipy algorithm on host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(wname, w, budget_s=30.0, iters_hint=None):
-    """Time a bounded sample of the workload with the CPU oracle (all BLAS threads).  Returns dict."""
-    import workloads
-    a, th0 = build_problem(w)
-    orc, m = oracle_model(a)
-    theta = workloads.perturbed_sets(th0, 64, w["seed"])
-    cores = os.cpu_count()
-    t_start = time.perf_counter()
-    if w["N"] >= 1024:
-        # one ELBOaux iteration of one set; an evaluation is setup + (n_it + 1) of these (meanfield.py:627-636)
-        mb = orc.model_with_hyper(m, theta[0])
+def reference_iterations(w):
+    """Iteration count of pool set 0 as run by the UNMODIFIED reference (tests/golden/big, generated once by
+    tests/golden/make_golden.py --big-converged).  None when no such record exists."""
+    if not w.get("anchor"):
+        return None
+    try:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "big", w["anchor"] + ".npz"))
+        return int(z["iters"]), float(z["elbo"])
+    except Exception:
+        return None
+
+
+class CpuArm:
+    """Bounded CPU samples of the workload with the oracle port (numpy / scipy on all BLAS threads).
+
+    N < 1024: a sample is the full ``ELBOcalc`` of the next pool set(s), the same sets the GPU arm evaluates.
+    N >= 1024 (one ELBOaux of the full model takes ~30 s on 16 cores): a sample is ONE ELBOaux iteration of a
+    two-matrix sub-model of pool set 0 at the full N (node 0, weight 0 -> output 0: the per-matrix cost of the
+    reference's algorithm -- LU solve with N right-hand sides, GEMM, Cholesky of Sigma, cho_solve with N right-hand
+    sides -- is the same for every matrix), scaled by M/2; an evaluation is the set-up plus (n_it + 1) such
+    iterations (meanfield.py:627-636), n_it being the iteration count of that set under the unmodified reference."""
+
+    def __init__(self, w, world=1):
+        import workloads
+        from oracle import gprn_oracle as orc
+        self.w, self.orc = w, orc
+        self.a, self.th0 = build_problem(w)
+        self.theta = workloads.perturbed_sets(self.th0, max(w["pool_per_gpu"], 1), w["seed"])
+        self.cores = os.cpu_count()
+        self.m = orc.Model(self.a["t"], self.a["y"], self.a["yerr"], self.a["nodes"], self.a["weights"], None,
+                           self.a["jitters"])
+        self.cursor = 0
+        self.big = w["N"] >= 1024
+        self.evals_s = []
+        if self.big:
+            mb = orc.model_with_hyper(self.m, self.theta[0])
+            sub = orc.Model(self.a["t"], self.a["y"][:1], self.a["yerr"][:1], [mb.nodes[0]], [mb.weights[0]], None,
+                            mb.jitters[:1])
+            t0 = time.perf_counter()
+            self.mats = orc.build_matrices(sub)
+            self.state = orc.init_mu_var(sub)
+            self.t_setup2 = time.perf_counter() - t0
+            self.sub = sub
+            rec = reference_iterations(w)
+            self.n_it, self.n_it_src = (rec[0], "iteration count of this set under the unmodified reference, "
+                                        "tests/golden/big/%s.npz" % w["anchor"]) if rec else (50, "iteration count assumed")
+
+    def sample(self):
+        """One bounded sample; returns (evals/s estimate, seconds spent)."""
+        orc, w = self.orc, self.w
         t0 = time.perf_counter()
-        Kf, Kw, Lf, Lw = orc.build_matrices(mb)
-        mu, var = orc.init_mu_var(mb)
-        t_setup = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        orc.elbo_aux(mb, Kf, Kw, Lf, Lw, mb.y - mb.mean_vals, mb.jitters ** 2, mu, var)
-        t_aux = time.perf_counter() - t0
-        src = "iteration count of this set from the GPU run beside it"
-        if not iters_hint:
-            try:    # counts recorded by tools/record_iterations.py on a B200 (parity tests: counts equal the reference's)
-                iters_hint = int(json.load(open(os.path.join(ROOT, "profiles", f"iterations_{wname}.json")))["iterations"][0])
-                src = f"iteration count of this set recorded in profiles/iterations_{wname}.json"
-            except Exception:
-                iters_hint, src = 50, "iteration count assumed"
-        n_it = iters_hint
-        per_eval = t_setup + (n_it + 1) * t_aux
-        return {"value": 1.0 / per_eval, "unit": "elbo_evals/s", "cores": cores, "kind": "port",
-                "sample": f"1 set: setup {t_setup:.1f} s + 1 ELBOaux iteration {t_aux:.1f} s measured; evaluation = setup + "
-                          f"(n_it+1) iterations with n_it={n_it} ({src}); "
-                          f"numpy/scipy oracle port of the reference algorithm, OpenBLAS threads={cores}",
-                "seconds": time.perf_counter() - t_start}
-    done, its = 0, 0
-    while done < len(theta) and (time.perf_counter() - t_start) < budget_s:
-        mb = orc.model_with_hyper(m, theta[done])
-        try:
-            _, _, _, it = orc.elbo_calc(mb)
-            its += it
-        except np.linalg.LinAlgError:
-            pass
-        done += 1
-    dt = time.perf_counter() - t_start
-    return {"value": done / dt, "unit": "elbo_evals/s", "cores": cores, "kind": "port",
-            "sample": f"first {done} hyper sets of the workload, full ELBOcalc each (mean {its / max(done, 1):.1f} iterations), "
-                      f"numpy/scipy oracle port of the reference algorithm, OpenBLAS threads={cores}",
-            "seconds": dt}
+        if self.big:
+            Kf, Kw, Lf, Lw = self.mats
+            mu, var = self.state
+            orc.elbo_aux(self.sub, Kf, Kw, Lf, Lw, self.sub.y - self.sub.mean_vals, self.sub.jitters ** 2, mu, var)
+            dt = time.perf_counter() - t0
+            M = w["q"] * (w["p"] + 1)
+            per_eval = (M / 2.0) * (self.t_setup2 + (self.n_it + 1) * dt)
+            v = 1.0 / per_eval
+        else:
+            n = 0
+            while n < 2:
+                mb = orc.model_with_hyper(self.m, self.theta[self.cursor % len(self.theta)])
+                self.cursor += 1
+                try:
+                    orc.elbo_calc(mb)
+                except np.linalg.LinAlgError:
+                    pass
+                n += 1
+            dt = time.perf_counter() - t0
+            v = n / dt
+        self.evals_s.append(v)
+        return v, dt
+
+    def describe(self):
+        if self.big:
+            return (f"per sample: one ELBOaux iteration of a 2-matrix sub-model (node 0, weight 0) of pool set 0 at N="
+                    f"{self.w['N']}, scaled by M/2; evaluation = set-up + (n_it+1) iterations, n_it={self.n_it} "
+                    f"({self.n_it_src}); numpy/scipy oracle port of the reference algorithm, BLAS threads={self.cores}")
+        return (f"per sample: full ELBOcalc of the next 2 pool sets (the sets the GPU arm evaluates, in order); "
+                f"numpy/scipy oracle port of the reference algorithm, BLAS threads={self.cores}")
 
 
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    t0 = time.perf_counter()
-    samples = []
-    total = args.warmup + args.steps
-    budget = 240.0
-    for s in range(total):
-        if s > 0 and time.perf_counter() - t0 > budget:
-            break
-        r = cpu_sample(args.workload, w, budget_s=20.0 if w["N"] < 1024 else 0.0)
-        if s >= min(args.warmup, total - 1) or s == total - 1:
-            samples.append(r)
-    vals = [r["value"] for r in samples]
-    v = float(np.mean(vals))
-    out = {"metric": "elbo_evals_per_sec", "value": v, "unit": "elbo_evals/s", "n_gpus": args.gpus, "steps": len(samples),
-           "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([r["seconds"] for r in samples])),
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "impl": "reference", "config": {"workload": w["name"], "sets_per_gpu": w["sets_per_gpu"]},
-           "cpu_baseline": {"value": v, "unit": "elbo_evals/s", "cores": samples[-1]["cores"], "kind": "port",
-                            "sample": samples[-1]["sample"]},
+    world = args.gpus
+    t_start = time.perf_counter()
+    arm = CpuArm(w)
+    arm.sample()                                      # one untimed sample: BLAS thread pool spin-up, page faults
+    arm.evals_s.clear()
+    secs = []
+    for _ in range(args.steps):
+        v, dt = arm.sample()
+        secs.append(dt)
+    v = float(np.mean(arm.evals_s))
+    cfg = config_of(args, w, world)
+    out = {"metric": "elbo_evals_per_sec", "value": v, "unit": "elbo_evals/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
+           "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "impl": "reference", "config": cfg,
+           "cpu_baseline": {"value": v, "unit": "elbo_evals/s", "cores": arm.cores, "kind": "port",
+                            "sample": arm.describe() + "; 1 untimed sample first, CPU timing has no other warm-up"},
            "e2e": {"value": v, "unit": "elbo_evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0}
+           "gpu_launches": 0, "run": {"wall_s": time.perf_counter() - t_start,
+                                      "omp_num_threads": os.environ.get("OMP_NUM_THREADS")}}
     print(json.dumps(out), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def make_inference(a, w, device):
+    import gpyrn_b200 as gp
+    from gpyrn_b200 import covfunc, meanfunc
+    KC = {"QP": covfunc.QuasiPeriodic, "M52": covfunc.Matern52, "SE": covfunc.SquaredExponential}
+    ya = []
+    for y, e in zip(a["y"], a["yerr"]):
+        ya += [y, e]
+    g = gp.inference(w["q"], a["t"], *ya, device=device)
+    g.set_components([KC[s[0]](*s[1:]) for s in a["nodes"]], [KC[s[0]](*s[1:]) for s in a["weights"]],
+                     [meanfunc.Constant(0.0)] * w["p"], [0.1] * w["p"])
+    return g
+
+
+def traffic_model(wname, N, iters_total, evals):
+    """DRAM bytes of a step from the ncu capture of this workload (profiles/traffic_<w>_r02.json: bytes per
+    set-iteration and per set-up, dram__bytes_read.sum + dram__bytes_write.sum over every kernel).  None without it."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", f"traffic_{wname}_r02.json")))
+        return float(d["dram_bytes_per_set_iteration"]) * iters_total + float(d["dram_bytes_per_setup"]) * evals
+    except Exception:
+        return None
+
+
 def run_ours(args, w):
+    import ctypes
     import torch
     import torch.distributed as dist
-    import gpyrn_b200 as gp
-    from gpyrn_b200 import _lib, covfunc, meanfunc, distributed as D
+    from gpyrn_b200 import _lib, distributed as D
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -209,64 +302,37 @@ def run_ours(args, w):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import workloads
     a, th0 = build_problem(w)
     N, p, q = w["N"], w["p"], w["q"]
-    B_local = args.sets_per_gpu or w["sets_per_gpu"]
-    B = B_local * world
-    # Equal-work shards: the sets differ a lot in cost (C4: 34...94 iterations), so a fair weak-scaling series needs
-    # per-GPU work that does not depend on N.  With recorded iteration counts (profiles/iterations_<w>.json, written by
-    # tools/record_iterations.py) the pool of 8 x sets_per_gpu sets is cut into 8 blocks of equal summed cost; rank r
-    # always evaluates block r, whatever N is.  Without the record: round-robin shards, re-dealt after the warm-up.
-    pool_B = B_local * max(8, world)
-    theta = workloads.perturbed_sets(th0, pool_B, w["seed"])
-    blocks = None
-    try:
-        recd = json.load(open(os.path.join(ROOT, "profiles", f"iterations_{args.workload}.json")))
-        rec = recd["iterations"]
-        if len(rec) >= pool_B and not args.no_balance:
-            # lock-step cost model (time of one iteration with 1..k active sets, measured): a block that ends in a
-            # long single-set tail costs more than its iteration sum says
-            st = recd.get("lockstep_ms") if B_local == len(recd.get("lockstep_ms", [])) else None
-            blocks = D.balanced_assignment(rec[:pool_B], pool_B // B_local, step_times=st)
-            # blocks have (nearly) equal cost; order them by the distance of their cost from the mean so that block 0
-            # -- the N = 1 workload -- is the most typical one and small N stay representative of the pool
-            cost = [D.lockstep_cost([rec[i] for i in b], st) if st else float(sum(rec[i] for i in b)) for b in blocks]
-            mean = sum(cost) / len(cost)
-            blocks = [b for _, _, b in sorted(zip([abs(c - mean) for c in cost], range(len(blocks)), blocks),
-                                              key=lambda x: (x[0], x[1]))]
-    except Exception:
-        blocks = None
-    if blocks is not None:
-        idx = blocks[rank]
-        used = np.sort(np.concatenate(blocks[:world]))
-    else:
-        idx = D.shard_indices(B, world, rank, "strided")
-        used = np.arange(B)
-    theta_l = np.ascontiguousarray(theta[idx])
-    KC = {"QP": covfunc.QuasiPeriodic, "M52": covfunc.Matern52, "SE": covfunc.SquaredExponential}
-    ya = []
-    for y, e in zip(a["y"], a["yerr"]):
-        ya += [y, e]
-    g = gp.inference(q, a["t"], *ya, device=local)
-    g.set_components([KC[s[0]](*s[1:]) for s in a["nodes"]], [KC[s[0]](*s[1:]) for s in a["weights"]],
-                     [meanfunc.Constant(0.0)] * p, [0.1] * p)
-    P_l = np.concatenate([theta_l[:, :-p], np.zeros((B_local, p)), theta_l[:, -p:]], axis=1)
+    theta, base = pool_of(w, th0, world, args.scaling, args.pool)
+    B, H = theta.shape
+    slots = args.slots if args.slots else w["slots"]
+    g = make_inference(a, w, local)
+    P = np.concatenate([theta[:, :-p], np.zeros((B, p)), theta[:, -p:]], axis=1)      # get_parameters order
     L = _lib.lib()
     h = g._h()
     g._bind_model(g.nodes, g.weights)
     _lib.check(L.gprn_upload_ysub(h, _lib.dptr(_lib.f64(a["y"]))))
-    H = theta_l.shape[1]
-    d_hyper = torch.from_numpy(theta_l).cuda()
-    d_elbo = torch.empty(B_local, dtype=torch.float64, device="cuda")
-    d_iters = torch.empty(B_local, dtype=torch.int32, device="cuda")
-    d_status = torch.empty(B_local, dtype=torch.int32, device="cuda")
+    d_hyper = torch.from_numpy(theta).cuda()
+    d_elbo = torch.zeros(B, dtype=torch.float64, device="cuda")
+    d_iters = torch.zeros(B, dtype=torch.int32, device="cuda")
+    d_status = torch.zeros(B, dtype=torch.int32, device="cuda")
+    d_taken = torch.zeros(B, dtype=torch.int32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream()
+    serial = [0]
 
     def step_dev():
-        _lib.check(L.gprn_elbo_batched_dev(h, B_local, d_hyper.data_ptr(), -1, d_elbo.data_ptr(), d_iters.data_ptr(),
-                                           d_status.data_ptr(), stream.cuda_stream))
+        """One step with the pool resident in HBM: dynamic dealing + the result all-reduce, all on `stream`."""
+        serial[0] += 1
+        counter = D.SharedCounter(B, f"dev{serial[0]}")
+        cb = _lib.NEXT_SET_FN(lambda _u: counter.next())
+        _lib.check(L.gprn_elbo_pool(h, B, d_hyper.data_ptr(), 1, None, 1, ctypes.cast(cb, ctypes.c_void_p), None, slots,
+                                    0, -1, d_elbo.data_ptr(), d_iters.data_ptr(), d_status.data_ptr(),
+                                    d_taken.data_ptr(), 1, stream.cuda_stream))
+        mine = d_taken.clone()
+        D.reduce_disjoint([d_elbo, d_iters, d_status, d_taken])       # the one collective of the path
+        return mine
 
     def barrier():
         if world > 1:
@@ -276,86 +342,212 @@ def run_ours(args, w):
     for _ in range(args.warmup):
         step_dev()
     barrier()
-    if world > 1 and blocks is None and not args.no_balance:
-        # re-deal the sets so that every rank carries the same summed iteration count (measured by the warm-up
-        # pass); counts per rank stay equal, so this is still weak scaling over the same global batch
-        it_all = D.gather_results(idx, {"iters": d_iters.cpu().numpy().astype(np.int64)}, pool_B)["iters"]
-        idx = used[D.balanced_assignment(it_all[used], world)[rank]]
-        theta_l = np.ascontiguousarray(theta[idx])
-        P_l = np.concatenate([theta_l[:, :-p], np.zeros((B_local, p)), theta_l[:, -p:]], axis=1)
-        d_hyper.copy_(torch.from_numpy(theta_l))
-        step_dev()
-        barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     L.gprn_reset_launch_count(h)
     ms = 0.0
+    rounds = 0
+    mine = None
     for _ in range(args.steps):
         flush.fill_(1)                                  # evict L2 between steps (outside the timed events)
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        step_dev()
+        mine = step_dev()
         e1.record(stream)
         e1.synchronize()
         ms += e0.elapsed_time(e1)
+        rounds += int(L.gprn_last_rounds(h))
     barrier()
     launches = int(L.gprn_launch_count(h))
-    iters_l = d_iters.cpu().numpy().astype(np.int64)
-    status_l = d_status.cpu().numpy()
-    elbo_l = d_elbo.cpu().numpy()
-    # end to end through the public API (host buffers in, host results out)
-    g.ELBO_batch(P_l[: max(1, min(B_local, 2))])
+    graph_launches = int(L.gprn_graph_launch_count(h))
+    iters_all = d_iters.cpu().numpy().astype(np.int64)
+    status_all = d_status.cpu().numpy()
+    elbo_all = d_elbo.cpu().numpy()
+    taken_all = d_taken.cpu().numpy()
+    mine = mine.cpu().numpy().astype(bool)
+    assert np.all(taken_all == 1), "every set of the pool must be evaluated by exactly one rank"
+    # end to end through the product API (host buffers in, host results out, dynamic dealing, gather included)
+    D.elbo_pool_sharded(g, P[:max(1, min(B, 2))], slots=slots, key="e2e-warm")
     barrier()
+    e2e_steps = args.steps if not args.e2e_steps else min(args.steps, args.e2e_steps)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e_api, it_api, st_api = g.ELBO_batch(P_l, return_info=True)
+    for k in range(e2e_steps):
+        e_api, it_api, st_api, owner = D.elbo_pool_sharded(g, P, slots=slots, key=f"e2e{k}")
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if sampler else None
-    assert np.array_equal(e_api, elbo_l), "public API and device-pointer entry disagree"
+    assert np.array_equal(e_api, elbo_all), "product API and device-pointer entry disagree"
+    assert np.array_equal(it_api, iters_all)
+    if args.scaling == "weak" and world > 1:
+        rep = elbo_all.reshape(world, base)
+        assert np.all(rep == rep[0]), "replicas of a set evaluated on different GPUs must agree bit for bit"
 
     t_ms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    fl = torch.tensor([algorithmic_flops(N, p, q, iters_l), float(iters_l.sum()), float(launches),
-                       float((status_l != 0).sum())], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(launches), float(graph_launches), float(mine.sum()), float(iters_all[mine].sum()),
+                        float(rounds)], dtype=torch.float64, device="cuda")
+    per_rank = torch.zeros(world, 3, dtype=torch.float64, device="cuda")
+    per_rank[rank] = torch.tensor([float(mine.sum()), float(iters_all[mine].sum()), ms], dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(fl, op=dist.ReduceOp.SUM)
-        # the one collective of the path: gather the ELBO values (NCCL over NVLink)
-        res = D.gather_results(idx, {"elbo": elbo_l, "iters": iters_l}, pool_B)
-        elbo_all = res["elbo"][used]
-    else:
-        elbo_all = elbo_l
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
     if rank == 0:
         ms_tot, e2e_ms = float(t_ms[0]), float(t_ms[1])
-        flops_step, iters_step, launches_all, bad = [float(x) for x in fl]
+        launches_all, graphs_all = float(cnt[0]), float(cnt[1])
         peak, peak_src = fp64_peak()
         value = B * args.steps / (ms_tot * 1e-3)
+        flops_step = algorithmic_flops(N, p, q, iters_all)
+        flops_min = algorithmic_flops(N, p, q, iters_all, cross=2.0 / 3.0)
         achieved = flops_step * args.steps / (ms_tot * 1e-3) / 1e12 / world      # per GPU
+        achieved_min = flops_min * args.steps / (ms_tot * 1e-3) / 1e12 / world
+        traffic = traffic_model(args.workload, N, float(iters_all.sum()), B)
+        anchor = None
+        rec = reference_iterations(w)
+        if rec:       # pool set 0 has a converged record of the unmodified reference: compare the run against it
+            anchor = {"set": 0, "elbo": float(elbo_all[0]), "elbo_reference": rec[1], "iters": int(iters_all[0]),
+                      "iters_reference": rec[0], "rel_err": abs(float(elbo_all[0]) - rec[1]) / abs(rec[1]),
+                      "source": "tests/golden/big/%s.npz (unmodified reference, converged)" % w["anchor"]}
+        cfg = config_of(args, w, world)
         out = {"metric": "elbo_evals_per_sec", "value": value, "unit": "elbo_evals/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_tot / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": w["name"], "N": N, "p": p, "q": q, "sets_per_gpu": B_local, "global_sets": B,
-                          "mean_iterations": iters_step / B, "elbo_iterations_per_sec": iters_step * args.steps / (ms_tot * 1e-3),
-                          "not_converged_or_failed": int(bad),
-                          "sharding": ("equal-cost blocks from recorded iteration counts and the measured lock-step iteration times (profiles/iterations_%s.json); rank r always evaluates block r" % args.workload)
-                          if blocks is not None else ("round-robin" if (world == 1 or args.no_balance) else
-                                                      "round-robin, re-dealt by warm-up iteration counts (equal sets per rank)"),
-                          "l2": "256 MiB flush between steps; per-step working set (K, L, L^-1 per matrix) >> 126 MB L2",
-                          "elbo_checksum": float(np.sum(elbo_all))},
-               "e2e": {"value": B * args.steps / (e2e_ms * 1e-3), "unit": "elbo_evals/s",
-                       "h2d_bytes_per_step": int(B_local * H * 8 + p * N * 8), "d2h_bytes_per_step": int(B_local * 16)},
-               "gpu_launches": int(launches_all),
+               "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+               "run": {"slots_per_gpu": slots if slots else "all that fit", "mean_iterations": float(iters_all.mean()),
+                       "elbo_iterations_per_sec": float(iters_all.sum()) * args.steps / (ms_tot * 1e-3),
+                       "not_converged_or_failed": int((status_all != 0).sum()),
+                       "dealing": "dynamic: shared counter on the rendezvous store, natural order; result all-reduce inside the timed step",
+                       "sets_per_rank_last_step": [int(x) for x in per_rank[:, 0].tolist()],
+                       "iterations_per_rank_last_step": [int(x) for x in per_rank[:, 1].tolist()],
+                       "device_ms_per_rank": [float(x) for x in per_rank[:, 2].tolist()],
+                       "lockstep_rounds_per_step": float(cnt[4]) / args.steps / world,
+                       "l2": "256 MiB flush between steps; per-step working set (K, L, L^-1 per matrix) >> 126 MB L2"
+                             if N >= 1024 or B > 64 else "256 MiB flush between steps",
+                       "elbo_checksum": float(np.sum(elbo_all)), "anchor": anchor},
+               "e2e": {"value": B * e2e_steps / (e2e_ms * 1e-3), "unit": "elbo_evals/s", "steps": e2e_steps,
+                       "h2d_bytes_per_step": int(B * H * 8 + p * N * 8), "d2h_bytes_per_step": int(B * 20),
+                       "api": "gpyrn_b200.distributed.elbo_pool_sharded -> inference.ELBO_batch (host buffers)"},
+               "gpu_launches": int(launches_all), "graph_launches": int(graphs_all),
                "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                            "traffic": None, "peak_source": "FP64 " + peak_src,
-                            "what": "whole batched evaluation, algorithmic FP64 flops (SURVEY.md 8d) / device time, per GPU"},
+                            "frac_executed_min": achieved_min / peak, "traffic": traffic, "peak_source": "FP64 " + peak_src,
+                            "what": "whole batched evaluation, algorithmic FP64 flops (SURVEY.md 8d) / device time, per GPU; "
+                                    "frac_executed_min counts the cross-node trace at (2/3) N^3 per pair (what the kernel "
+                                    "executes) instead of the survey's N^3; traffic = DRAM bytes per step of all kernels "
+                                    "(ncu, profiles/traffic_%s_r02.json) or null" % args.workload},
                "clocks": clocks}
         if world == 1 and not args.no_cpu:
-            hint = int(iters_l[0]) if (N >= 1024 and blocks is None) else None   # set 0 is what the CPU leg times
-            cb = cpu_sample(args.workload, w, budget_s=20.0, iters_hint=hint)
-            cb.pop("seconds", None)
-            out["cpu_baseline"] = cb
+            arm = CpuArm(w)
+            t0 = time.perf_counter()
+            arm.sample()
+            arm.evals_s.clear()
+            while time.perf_counter() - t0 < 25.0 or not arm.evals_s:
+                arm.sample()
+            out["cpu_baseline"] = {"value": float(np.mean(arm.evals_s)), "unit": "elbo_evals/s", "cores": arm.cores,
+                                   "kind": "port", "sample": f"{len(arm.evals_s)} samples; " + arm.describe()}
+        print(json.dumps(out), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# C5: lock-step multi-start optimisation + prediction on 20 000 test epochs
+# ------------------------------------------------------------------------------------------------
+def run_c5(args, w):
+    import torch
+    import torch.distributed as dist
+    import workloads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    a, th0 = build_problem(w)
+    N, p, q = w["N"], w["p"], w["q"]
+    M = q * (p + 1)
+    S_g = args.pool if args.pool and args.scaling == "weak" else w["pool_per_gpu"]
+    S = S_g * world
+    theta = workloads.perturbed_sets(th0, S, w["seed"])
+    mine = np.arange(rank, S, world)                     # a start's variational state lives on one GPU: static deal
+    g = make_inference(a, w, local)
+    g.freeze_parameter(name='mean*')                     # Constant(0) means stay fixed: sweep over kernel pars + jitters
+    L = __import__("gpyrn_b200")._lib.lib()
+    h = g._h()
+    maxfev = args.maxfev
+    t = a["t"]
+    span = t[-1] - t[0]
+    tstar = np.linspace(t[0] - 0.2 * span, t[-1] + 0.2 * span, 20000)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def sweep():
+        res = g.optimize_batch(theta[mine], options={"maxfev": maxfev, "xatol": 1e-4, "fatol": 1e-4})
+        return res, g.n_batch_calls
+
+    # warm-up: a short sweep (graph capture, workspace allocation) and one prediction
+    g.optimize_batch(theta[mine][:2], options={"maxfev": 3})
+    g.ELBOcalc()
+    g._Prediction(tstar=tstar[:4096])
+    barrier()
+    L.gprn_reset_launch_count(h)
+    t0 = time.perf_counter()
+    sweeps = []
+    for _ in range(args.steps):
+        sweeps.append(sweep())
+    torch.cuda.synchronize()
+    t_opt = time.perf_counter() - t0
+    barrier()
+    res, ncalls = sweeps[-1]
+    fun = np.array([r.fun for r in res])
+    nfev = np.array([r.nfev for r in res])
+    # best start of this rank -> converge its state once more and predict at T = 20000 (device time by CUDA events)
+    best = int(np.argmin(fun))
+    g.set_parameters(res[best].x)
+    elbo, mu, var, it = g.ELBOcalc()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tp0 = time.perf_counter()
+    e0.record()
+    pm, pv = g._Prediction(tstar=tstar, mu=mu, var=var)
+    e1.record()
+    torch.cuda.synchronize()
+    tp = time.perf_counter() - tp0
+    launches = int(L.gprn_launch_count(h))
+    tt = torch.tensor([t_opt, tp], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(nfev.sum()), float(launches), float(-fun.min())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        mx = cnt[2:].clone()
+        dist.all_reduce(cnt[:2], op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        cnt[2] = mx[0]
+    if rank == 0:
+        peak, peak_src = fp64_peak()
+        f_pred = M * (N ** 3 / 3.0 + float(N) ** 2 * 20000)
+        t_opt_all, t_pred = float(tt[0]), float(tt[1])
+        out = {"metric": "optimisations_per_sec", "value": S * args.steps / t_opt_all, "unit": "optimisations/s",
+               "n_gpus": world, "steps": args.steps, "warmup": 1, "ms_per_step": 1e3 * t_opt_all / args.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": w["name"], "N": N, "p": p, "q": q, "starts_per_gpu": S_g, "starts": S,
+                          "optimizer": f"scipy Nelder-Mead, maxfev={maxfev}, lock-step over the starts of a GPU "
+                                       f"(inference.optimize_batch), warm-started nELBO per start (device-resident state)",
+                          "T": 20000},
+               "run": {"objective_evaluations": int(cnt[0]), "elbo_evals_per_sec": float(cnt[0]) / t_opt_all,
+                       "batched_device_calls_last_sweep": int(ncalls), "best_elbo": float(cnt[2]),
+                       "prediction_ms": 1e3 * t_pred, "prediction_finite": bool(np.all(np.isfinite(pm)) and np.all(pv > 0))},
+               "e2e": {"value": S * args.steps / t_opt_all, "unit": "optimisations/s",
+                       "h2d_bytes_per_step": int(cnt[0] / args.steps * (theta.shape[1] * 8)),
+                       "d2h_bytes_per_step": int(cnt[0] / args.steps * 20)},
+               "gpu_launches": int(cnt[1]),
+               "roofline": {"bound": "tensor", "achieved": f_pred / t_pred / 1e12, "peak": peak, "unit": "TFLOP/s",
+                            "frac": f_pred / t_pred / 1e12 / peak, "traffic": None, "peak_source": "FP64 " + peak_src,
+                            "what": "prediction at T=20000 through inference._Prediction (host buffers in / out): "
+                                    "F_pred = M (N^3/3 + N^2 T) / wall time (SURVEY.md 8d)"}}
         print(json.dumps(out), flush=True)
     g.close()
     if world > 1:
@@ -369,13 +561,20 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("GPRN_BENCH_WORKLOAD", "c4"), choices=sorted(WORKLOADS))
-    ap.add_argument("--sets-per-gpu", type=int, default=0)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--pool", type=int, default=64, help="strong scaling: sets in the fixed pool (c5: starts per GPU)")
+    ap.add_argument("--slots", type=int, default=0, help="evaluations in flight per GPU (0: workload default / all that fit)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="cap on the end-to-end steps (default: --steps)")
+    ap.add_argument("--maxfev", type=int, default=40, help="c5: objective evaluations per Nelder-Mead start")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-balance", action="store_true", help="keep the round-robin shards (no cost-balanced re-deal)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, w)
+        run_reference(args, w if args.workload != "c5" else WORKLOADS["c5"])
+    elif args.workload == "c5":
+        if args.pool == 64 and args.scaling == "weak":
+            args.pool = 0
+        run_c5(args, w)
     else:
         run_ours(args, w)
 

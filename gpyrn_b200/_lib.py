@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("GPRN_B200_LIB", os.path.join(CSRC, "libgprn_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
+NEXT_SET_FN = ctypes.CFUNCTYPE(ctypes.c_int64, ctypes.c_void_p)      # gprn_next_set_fn
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
 
@@ -27,6 +28,7 @@ SIGNATURES = {
                                    c_double_p, ctypes.POINTER(ctypes.c_void_p)]),
     "gprn_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "gprn_set_workspace_limit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64]),
+    "gprn_set_max_slots": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "gprn_set_model": (ctypes.c_int, [ctypes.c_void_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p, ctypes.c_int]),
     "gprn_elbo_batched": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p, c_double_p, ctypes.c_int,
                                          ctypes.c_int, c_double_p, c_double_p, ctypes.c_int, c_double_p, c_int32_p,
@@ -34,6 +36,15 @@ SIGNATURES = {
     "gprn_upload_ysub": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
     "gprn_elbo_batched_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "gprn_elbo_pool": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, c_double_p,
+                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_int, ctypes.c_void_p]),
+    "gprn_chain_resize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
+    "gprn_chain_set": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, c_double_p, c_double_p]),
+    "gprn_chain_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, c_double_p, c_double_p,
+                                      c_int32_p]),
+    "gprn_chain_invalidate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]),
     "gprn_kmatrix": (ctypes.c_int, [ctypes.c_void_p, c_int32_p, ctypes.c_int, c_double_p, ctypes.c_int, c_double_p,
                                     ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_double, c_double_p,
                                     ctypes.c_void_p]),
@@ -41,10 +52,17 @@ SIGNATURES = {
                                   ctypes.c_int64, ctypes.c_int64, ctypes.c_int, c_double_p]),
     "gprn_predict": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, ctypes.c_int,
                                     c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, ctypes.c_void_p]),
+    "gprn_predict_batched": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p, c_double_p, c_double_p,
+                                            c_double_p, ctypes.c_int, c_double_p, ctypes.c_int, c_double_p, c_double_p,
+                                            c_double_p, c_double_p, ctypes.c_void_p]),
     "gprn_sample": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_double, c_double_p,
                                    ctypes.c_void_p]),
     "gprn_debug_factor": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p, c_double_p, c_double_p,
                                          c_double_p]),
+    "gprn_debug_panel_stress": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_int,
+                                               ctypes.POINTER(ctypes.c_int64)]),
+    "gprn_graph_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "gprn_last_rounds": (ctypes.c_int64, [ctypes.c_void_p]),
     "gprn_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "gprn_reset_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
     "gprn_last_elbo_ms": (ctypes.c_double, [ctypes.c_void_p]),

@@ -24,6 +24,9 @@ OP_CONST, OP_RQP, OP_COS, OP_EXP = 8, 9, 10, 11
 OP_DSE, OP_DPER, OP_DQP = 12, 13, 14
 
 
+default_device = -1     # GPU used by k(r) on the host-side kernel objects; -1: the thread's current device
+
+
 class covFunction:
     """Base class: a parameter vector plus a device program."""
     _opcode = None
@@ -48,7 +51,8 @@ class covFunction:
         prog = np.array(self.program(), dtype=np.int32)
         pars = _lib.f64(self.pars)
         out = np.empty_like(r2)
-        _lib.check(_lib.lib().gprn_keval(0, _lib.iptr(prog), prog.size, _lib.dptr(pars), pars.size,
+        # device -1: the calling thread's current CUDA device (the GPU of the inference object created last)
+        _lib.check(_lib.lib().gprn_keval(default_device, _lib.iptr(prog), prog.size, _lib.dptr(pars), pars.size,
                                          _lib.dptr(r2), r2.shape[0], r2.shape[1], square, _lib.dptr(out)))
         return out.reshape(shape)
 

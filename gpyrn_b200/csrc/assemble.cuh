@@ -136,18 +136,22 @@ __device__ __forceinline__ double eval_prog(const int32_t* __restrict__ tok, int
 }
 
 // Symmetric assembly of K_m = k_m(t - t^T) + nugget*I for every matrix of every set in the chunk.
-// grid = (nt*(nt+1)/2 lower tiles, M, nset), block = 256.  Writes tiles I >= J; diagonal tiles full.
-// Padding (index >= N): identity.
+// grid = (nt*(nt+1)/2 lower tiles, M, number of slots), block = 256.  Writes tiles I >= J; diagonal tiles full.
+// Padding (index >= N): identity.  slots: workspace slots to assemble (null: slot = blockIdx.z);
+// slot_set: row of `hyper` that each slot holds (null: the slot index itself).
 __global__ void __launch_bounds__(256) kassemble_sym_kernel(double* __restrict__ K, const double* __restrict__ time,
                                                             const double* __restrict__ hyper, int H, ProgTable pt,
-                                                            int M, int N, int Np, double nugget) {
+                                                            int M, int N, int Np, double nugget,
+                                                            const int* __restrict__ slots,
+                                                            const int* __restrict__ slot_set) {
     GPRN_TRACE_SCOPE(TK_KASSEMBLE);
     __shared__ double ti[NB], tj[NB];
     __shared__ int32_t stok[GPRN_MAX_PROG];
     __shared__ double spar[GPRN_MAX_PROG * 4];
     int I, J;
     tri_decode(blockIdx.x, I, J);
-    const int m = blockIdx.y, set = blockIdx.z;
+    const int m = blockIdx.y, set = slots ? slots[blockIdx.z] : (int)blockIdx.z;
+    const int hrow = slot_set ? slot_set[set] : set;
     const int tid = threadIdx.x;
     const int ntok = pt.len[m];
     if (tid < NB) {
@@ -158,46 +162,66 @@ __global__ void __launch_bounds__(256) kassemble_sym_kernel(double* __restrict__
     if (tid < ntok) stok[tid] = pt.tok[m * GPRN_MAX_PROG + tid];
     if (tid < GPRN_MAX_PROG * 4) {
         int po = pt.par_off[m] + tid;
-        spar[tid] = po < H ? hyper[(size_t)set * H + po] : 0.0;
+        spar[tid] = po < H ? hyper[(size_t)hrow * H + po] : 0.0;
     }
     __syncthreads();
     double* Kt = K + ((size_t)set * M + m) * Np * Np;
-    const int c = tid & 63, rg = tid >> 6;
-    const int gj = J * NB + c;
-#pragma unroll 4
-    for (int u = 0; u < 16; u++) {
-        const int rr = rg * 16 + u, gi = I * NB + rr;
-        double v;
+    // thread = two adjacent columns x 8 rows: a warp stores one full 512-byte tile row per instruction (16-byte stores)
+    const int c2 = tid & 31, rg = tid >> 5;
+    const int gj = J * NB + 2 * c2;
+#pragma unroll 2
+    for (int u = 0; u < 8; u++) {
+        const int rr = rg * 8 + u, gi = I * NB + rr;
+        double2 v;
         if (gi < N && gj < N) {
-            v = eval_prog(stok, ntok, spar, ti[rr] - tj[c], gi == gj, false);
-            if (gi == gj) v += nugget;
+            v.x = eval_prog(stok, ntok, spar, ti[rr] - tj[2 * c2], gi == gj, false);
+            if (gi == gj) v.x += nugget;
         } else {
-            v = (gi == gj) ? 1.0 : 0.0;
+            v.x = (gi == gj) ? 1.0 : 0.0;
         }
-        Kt[(size_t)gi * Np + gj] = v;
+        if (gi < N && gj + 1 < N) {
+            v.y = eval_prog(stok, ntok, spar, ti[rr] - tj[2 * c2 + 1], gi == gj + 1, false);
+            if (gi == gj + 1) v.y += nugget;
+        } else {
+            v.y = (gi == gj + 1) ? 1.0 : 0.0;
+        }
+        *reinterpret_cast<double2*>(Kt + (size_t)gi * Np + gj) = v;
     }
 }
 
 // Rectangular assembly K[r][c] = k(trow[r] - tcol[c]) (+ nugget on the diagonal when `square`),
-// row-major with leading dimension ld, no padding.  grid = (ceil(ncols/64), ceil(nrows/64)), block 256.
-// Used for Kstar (prediction) and for gprn_kmatrix.
+// row-major with leading dimension ld, no padding.  grid = (ceil(ncols/64), ceil(nrows/64), nbatch), block 256.
+// Used for Kstar (prediction) and for gprn_kmatrix.  `row0`: index of trow[0] in the caller's full row range (the
+// diagonal-by-position rule of WhiteNoise, quirk Q9, applies to global positions when rows are processed in chunks).
+// Batched form (blockIdx.z = b): matrix b is written at K + b*kstride and uses program / parameter set
+// tokb[b*GPRN_MAX_PROG..], lenb[b], parb + paroff[b]; with tokb == null the single (tok, ntok, par) is used.
 __global__ void __launch_bounds__(256) kassemble_rect_kernel(double* __restrict__ K, size_t ld,
                                                              const double* __restrict__ trow, int nrows,
                                                              const double* __restrict__ tcol, int ncols,
                                                              const int32_t* __restrict__ tok, int ntok,
                                                              const double* __restrict__ par, int npar, int square,
-                                                             double nugget) {
+                                                             double nugget, int row0, size_t kstride,
+                                                             const int32_t* __restrict__ lenb,
+                                                             const int32_t* __restrict__ paroff) {
     __shared__ double ti[NB], tj[NB];
     __shared__ int32_t stok[GPRN_MAX_PROG];
     __shared__ double spar[GPRN_MAX_PROG * 4];
     const int tid = threadIdx.x;
+    int poff = 0;
+    if (lenb) {                    // batched: per-matrix program; parameters at par[paroff[b] ..] of an npar-long vector
+        const int b = blockIdx.z;
+        tok += (size_t)b * GPRN_MAX_PROG;
+        ntok = lenb[b];
+        poff = paroff[b];
+        K += (size_t)b * kstride;
+    }
     if (tid < NB) {
         int gi = blockIdx.y * NB + tid, gj = blockIdx.x * NB + tid;
         ti[tid] = gi < nrows ? trow[gi] : 0.0;
         tj[tid] = gj < ncols ? tcol[gj] : 0.0;
     }
     if (tid < ntok) stok[tid] = tok[tid];
-    if (tid < GPRN_MAX_PROG * 4) spar[tid] = tid < npar ? par[tid] : 0.0;
+    if (tid < GPRN_MAX_PROG * 4) spar[tid] = poff + tid < npar ? par[poff + tid] : 0.0;
     __syncthreads();
     const int c = tid & 63, rg = tid >> 6;
     const int gj = blockIdx.x * NB + c;
@@ -205,8 +229,8 @@ __global__ void __launch_bounds__(256) kassemble_rect_kernel(double* __restrict_
     for (int u = 0; u < 16; u++) {
         const int rr = rg * 16 + u, gi = blockIdx.y * NB + rr;
         if (gi >= nrows) break;
-        double v = eval_prog(stok, ntok, spar, ti[rr] - tj[c], square && gi == gj, !square);
-        if (square && gi == gj) v += nugget;
+        double v = eval_prog(stok, ntok, spar, ti[rr] - tj[c], square && gi + row0 == gj, !square);
+        if (square && gi + row0 == gj) v += nugget;
         K[(size_t)gi * ld + gj] = v;
     }
 }

@@ -222,14 +222,120 @@ __device__ __forceinline__ void subst_lower_mma(const double* __restrict__ Ls, i
     }
 }
 
-// Cholesky of a 64x64 tile by 256 threads with the tile held in registers (thread (r, q4) owns row r,
-// columns q4 + 4u).  Outer-product form on UNSCALED columns (T[r][c] = L[r][c] * L[c][c], pivot = L[c][c]^2),
-// so a step needs one barrier: the owners of column c+1 publish it to shared memory as soon as step c has
-// updated it.  Scaling by 1/sqrt(pivot) happens once at the end.
+// Cholesky of a 64x64 tile by 256 threads.  Two implementations with the same contract:
 //   Td  : input tile in shared memory, element (m,n) at Td[m*ldd + n] (lower triangle used)
 //   Ls  : output, lower-triangular L with zeros above the diagonal, stride LDT (may alias Td)
-//   rd  : output, 1 / L[c][c];   col: scratch 128 doubles;   pivs: scratch 64 doubles (pivots L[c][c]^2)
+//   rd  : output, 1 / L[c][c];   col: scratch 128 doubles (v1 only);   pivs: output, pivots L[c][c]^2
 //   bad : set to 1 when a pivot is not positive (caller zeroes it)
+//
+// potrf64 (default, "v2"): right-looking in 8 block steps of 8 columns -- 16 CTA barriers instead of 64.
+//   Phase A (warps 0-1, thread t = row t): every thread loads the 8x8 diagonal block (broadcast reads) and factors
+//     it redundantly in registers on UNSCALED columns (T[i][k] = L[i][k] L[k][k], pivot p_k = L[k][k]^2: one
+//     reciprocal per pivot on the dependency chain, square roots off it), then solves its own row of the block
+//     column against it by forward substitution and writes the finished L row.
+//   Phase B (all 8 warps): the trailing 8x8 blocks (I >= K > j) get C_IK -= L_Ij L_Kj^T on DMMA m8n8k4.
+// A genuine substitution / factorisation: no inverse of a block is formed (DESIGN.md "Numerics").
+// Measured against v1 (one barrier per pivot, 64 x 290 ns = 19 us per tile): see profiles/README.md.
+#ifndef GPRN_POTRF_V1
+__device__ __forceinline__ void potrf64(const double* Td, int ldd, double* Ls, double* __restrict__ rd,
+                                        double* __restrict__ col, double* __restrict__ pivs, int* bad) {
+    (void)col;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (Td != Ls || ldd != LDT) {          // bring the tile into Ls with stride LDT (alias-safe)
+        const int r = tid >> 2, q4 = tid & 3;
+        double a[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) a[u] = Td[r * ldd + q4 + 4 * u];
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 16; u++) Ls[r * LDT + q4 + 4 * u] = a[u];
+        __syncthreads();
+    }
+#define GPRN_PT(u, w) T[(u) * ((u) + 1) / 2 + (w)]
+    for (int j = 0; j < 8; j++) {
+        const int c0 = 8 * j;
+        if (tid < NB) {                    // warps 0-1, converged: thread = row of the tile
+            double T[36], inv[8], a[8], y[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int w = 0; w <= u; w++) GPRN_PT(u, w) = Ls[(c0 + u) * LDT + c0 + w];
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(Ls + tid * LDT + c0 + k);
+                a[k] = v.x;
+                a[k + 1] = v.y;
+            }
+            // every read of the diagonal block precedes every write of this phase (rows c0..c0+7 are rewritten)
+            asm volatile("bar.sync 1, 64;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                inv[k] = __drcp_rn(GPRN_PT(k, k));
+#pragma unroll
+                for (int i = k + 1; i < 8; i++) {
+                    const double t = GPRN_PT(i, k) * inv[k];
+#pragma unroll
+                    for (int c = k + 1; c <= i; c++) GPRN_PT(i, c) = fma(-t, GPRN_PT(c, k), GPRN_PT(i, c));
+                }
+            }
+            // row solve  xs_k = a_k - sum_{c<k} (xs_c / p_c) T[k][c]   (xs_k = L[t][c0+k] L[c0+k][c0+k])
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+#pragma unroll
+                for (int c = 0; c < k; c++) a[k] = fma(-y[c], GPRN_PT(k, c), a[k]);
+                y[k] = a[k] * inv[k];
+            }
+            if (tid >= c0) {
+                const int u = tid - c0;    // 0..7: row of the diagonal block; >= 8: row below it
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const double p = GPRN_PT(k, k);
+                    const double sq = sqrt(p);
+                    const double rs = __drcp_rn(sq);
+                    double val = a[k] * rs;
+                    if (k == u) {
+                        val = sq;
+                        pivs[tid] = p;
+                        rd[tid] = rs;
+                        if (!(p > 0.0)) *bad = 1;
+                    }
+                    if (k > u) val = 0.0;
+                    Ls[tid * LDT + c0 + k] = val;
+                }
+            }
+        }
+        __syncthreads();
+        if (j < 7) {
+            const int nb = 7 - j, cnt = nb * (nb + 1) / 2;
+            const int r = lane >> 2, c = lane & 3;
+            for (int pi = warp; pi < cnt; pi += 8) {
+                int ii = 0, kk = pi;
+                while (kk > ii) { kk -= ii + 1; ii++; }
+                const int I = j + 1 + ii, K = j + 1 + kk;
+                double* cp = Ls + (8 * I + r) * LDT + 8 * K + 2 * c;
+                double2 cv = *reinterpret_cast<double2*>(cp);
+                double acc[2] = {cv.x, cv.y};
+                const double* ap = Ls + (8 * I + r) * LDT + c0 + c;
+                const double* bp = Ls + (8 * K + r) * LDT + c0 + c;
+                dmma884(acc, -ap[0], bp[0]);
+                dmma884(acc, -ap[4], bp[4]);
+                *reinterpret_cast<double2*>(cp) = make_double2(acc[0], acc[1]);
+            }
+            __syncthreads();
+        }
+    }
+#undef GPRN_PT
+    // blocks above the diagonal were never touched: they still hold the input's upper triangle
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e >> 6, c = e & 63;
+        if ((c >> 3) > (r >> 3)) Ls[r * LDT + c] = 0.0;
+    }
+    __syncthreads();
+}
+#else
+// potrf64 v1 (-DGPRN_POTRF_V1): tile held in registers (thread (r, q4) owns row r, columns q4 + 4u), outer-product
+// form on UNSCALED columns, one barrier per pivot: the owners of column c+1 publish it to shared memory as soon as
+// step c has updated it.  Scaling by 1/sqrt(pivot) happens once at the end.
 __device__ __forceinline__ void potrf64(const double* Td, int ldd, double* Ls, double* __restrict__ rd,
                                         double* __restrict__ col, double* __restrict__ pivs, int* bad) {
     const int tid = threadIdx.x, r = tid >> 2, q4 = tid & 3;
@@ -277,6 +383,7 @@ __device__ __forceinline__ void potrf64(const double* Td, int ldd, double* Ls, d
     }
     __syncthreads();
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Per-CTA execution trace (development aid, compiled in only with -DGPRN_TRACE; see tools/trace_run.py):

@@ -4,6 +4,10 @@
 // _expectedLogPrior (:1019-1065), _entropy (:1085-1093), ELBOcalc loop (:627-649), _initMuVar (:491-510),
 // written in the Sigma-free form of SURVEY.md Appendix A.3 (see DESIGN.md "Algorithm").
 //
+// Workspace slots: the engine (gprn_api.cu: run_pool) keeps `nslot` evaluations in flight; every per-set array
+// below is indexed by the SLOT, and slot_set[slot] names the set of the pool (row of `hyper` / `ysub`, entry of
+// the result arrays) that the slot currently works on.  "set" in the kernels below is the slot index.
+//
 // State layout per set (the reference's flat u, meanfield.py:487-488): mu[d], var[d] with
 // d = N*q*(p+1); nodes f[j][n] at j*N + n, weights w[i][j][n] at q*N + (i*q + j)*N + n.
 // Work vectors per matrix id (= set*M + m; m = j for nodes, q + j*p + i for weights): length Np,
@@ -17,9 +21,10 @@ struct ElboCtx {
     int N, Np, p, q, M, H, d;
     const double* yraw;    // [p][N]
     const double* yerr2;   // [p][N]
-    const double* ysub;    // [p][N] shared or [nset][p][N]
+    const double* ysub;    // [p][N] shared or [B][p][N] (indexed by the set a slot holds)
     int ysub_shared;
-    const double* hyper;   // [nset][H]
+    const double* hyper;   // [B][H] hyper-parameter sets of the whole pool
+    const int* slot_set;   // [nslot] pool index of the set each workspace slot currently holds
     const int32_t* par_off;  // [M]
     double *mu, *var;        // [nset][d] current state
     double *mu_new, *var_new;  // [nset][d]
@@ -35,49 +40,101 @@ struct ElboCtx {
     int max_iter;
 };
 
+__device__ __forceinline__ const double* hyper_of(const ElboCtx& c, int set) {
+    return c.hyper + (size_t)c.slot_set[set] * c.H;
+}
 __device__ __forceinline__ double variance_at(const ElboCtx& c, int set, int i, int n) {
-    double jit = c.hyper[(size_t)set * c.H + c.H - c.p + i];
+    double jit = hyper_of(c, set)[c.H - c.p + i];
     return jit * jit + c.yerr2[i * c.N + n];      // meanfield.py:759 (jitters**2 at :618)
 }
 __device__ __forceinline__ const double* ysub_of(const ElboCtx& c, int set) {
-    return c.ysub_shared ? c.ysub : c.ysub + (size_t)set * c.p * c.N;
+    return c.ysub_shared ? c.ysub : c.ysub + (size_t)c.slot_set[set] * c.p * c.N;
 }
 
-// _initMuVar (meanfield.py:491-510), written straight into the flat layout (quirk Q5 included).
-// grid = (nset), block = 256.
-__global__ void init_state_kernel(ElboCtx c) {
-    const int set = blockIdx.x;
-    const double* h = c.hyper + (size_t)set * c.H;
+// Admission of a set into a workspace slot.  The variational state starts from _initMuVar (meanfield.py:491-510,
+// written straight into the flat layout, quirk Q5 included) or, when the chain-state store holds a valid entry
+// for the set ('previous', meanfield.py:598-607), from that entry.  Also clears the per-matrix accumulators of the
+// slot (log-dets are accumulated by the factorisation kernels).  grid = (number of admitted slots), block = 256.
+struct ChainView {        // device view of a chain-state store (all null: no store)
+    double* mu;           // [n][d]
+    double* var;          // [n][d]
+    int* valid;           // [n]
+};
+__global__ void init_state_kernel(ElboCtx c, const int* __restrict__ slots, ChainView cs) {
+    const int set = slots[blockIdx.x];
+    const int idx = c.slot_set[set];
+    const double* h = hyper_of(c, set);
     double* mu = c.mu + (size_t)set * c.d;
     double* var = c.var + (size_t)set * c.d;
-    double jm = 0.0;
-    for (int i = 0; i < c.p; i++) jm += h[c.H - c.p + i];
-    jm = jm / c.p;
-    for (int e = threadIdx.x; e < c.q * c.N; e += blockDim.x) {
-        int j = e / c.N, n = e % c.N;
-        double a1 = h[c.par_off[j]];
-        double s = 0.0;
-        for (int i = 0; i < c.p; i++) {
-            double a2 = h[c.par_off[c.q + i]];       // only the first p weight amplitudes (zip truncation)
-            double y = c.yraw[i * c.N + n];
-            double sg = (y > 0.0) ? 1.0 : ((y < 0.0) ? -1.0 : 0.0);
-            s += sqrt((fabs(y) * a1) / a2) * sg;
+    if (cs.valid && cs.valid[idx]) {
+        const double* sm = cs.mu + (size_t)idx * c.d;
+        const double* sv = cs.var + (size_t)idx * c.d;
+        for (int e = threadIdx.x; e < c.d; e += blockDim.x) {
+            mu[e] = sm[e];
+            var[e] = sv[e];
         }
-        mu[e] = s / c.p;
-        var[e] = jm;
+    } else {
+        double jm = 0.0;
+        for (int i = 0; i < c.p; i++) jm += h[c.H - c.p + i];
+        jm = jm / c.p;
+        for (int e = threadIdx.x; e < c.q * c.N; e += blockDim.x) {
+            int j = e / c.N, n = e % c.N;
+            double a1 = h[c.par_off[j]];
+            double s = 0.0;
+            for (int i = 0; i < c.p; i++) {
+                double a2 = h[c.par_off[c.q + i]];       // only the first p weight amplitudes (zip truncation)
+                double y = c.yraw[i * c.N + n];
+                double sg = (y > 0.0) ? 1.0 : ((y < 0.0) ? -1.0 : 0.0);
+                s += sqrt((fabs(y) * a1) / a2) * sg;
+            }
+            mu[e] = s / c.p;
+            var[e] = jm;
+        }
+        for (int e = threadIdx.x; e < c.q * c.p * c.N; e += blockDim.x) {
+            int n = e % c.N, ji = e / c.N, j = ji / c.p, i = ji % c.p;   // written in (q,p,N) order
+            double a1 = h[c.par_off[j]];
+            double a2 = h[c.par_off[c.q + i]];
+            double y = c.yraw[i * c.N + n];
+            mu[c.q * c.N + e] = sqrt((fabs(y) * a2) / a1);
+            var[c.q * c.N + e] = h[c.H - c.p + i];          // jitter, not squared
+        }
     }
-    for (int e = threadIdx.x; e < c.q * c.p * c.N; e += blockDim.x) {
-        int n = e % c.N, ji = e / c.N, j = ji / c.p, i = ji % c.p;   // written in (q,p,N) order
-        double a1 = h[c.par_off[j]];
-        double a2 = h[c.par_off[c.q + i]];
-        double y = c.yraw[i * c.N + n];
-        mu[c.q * c.N + e] = sqrt((fabs(y) * a2) / a1);
-        var[c.q * c.N + e] = h[c.H - c.p + i];          // jitter, not squared
+    if (threadIdx.x < c.M) {
+        c.logdetK[(size_t)set * c.M + threadIdx.x] = 0.0;
+        c.mstatus[(size_t)set * c.M + threadIdx.x] = 0;
     }
     if (threadIdx.x == 0) {
         c.iters[set] = 0;
         c.status[set] = 0;
         c.active[set] = 1;
+    }
+}
+
+// Retirement of finished slots: results go to the pool-indexed output arrays; the final state goes back to the
+// chain-state store (commit = 2: always; 1: only when the evaluation converged, the reference's caching rule
+// meanfield.py:643-646; 0: never).  grid = (number of retired slots), block = 256.
+__global__ void retire_kernel(ElboCtx c, const int* __restrict__ slots, double* __restrict__ elbo_out,
+                              int* __restrict__ iters_out, int* __restrict__ status_out, int* __restrict__ taken_out,
+                              ChainView cs, int commit) {
+    const int set = slots[blockIdx.x];
+    const int idx = c.slot_set[set];
+    const int st = c.status[set];
+    if (threadIdx.x == 0) {
+        if (elbo_out) elbo_out[idx] = c.elbo[set];
+        if (iters_out) iters_out[idx] = c.iters[set];
+        if (status_out) status_out[idx] = st;
+        if (taken_out) taken_out[idx] = 1;
+    }
+    if (cs.mu && (commit == 2 || (commit == 1 && st == 0))) {
+        const double* mu = c.mu + (size_t)set * c.d;
+        const double* var = c.var + (size_t)set * c.d;
+        double* dm = cs.mu + (size_t)idx * c.d;
+        double* dv = cs.var + (size_t)idx * c.d;
+        for (int e = threadIdx.x; e < c.d; e += blockDim.x) {
+            dm[e] = mu[e];
+            dv[e] = var[e];
+        }
+        if (threadIdx.x == 0) cs.valid[idx] = 1;
     }
 }
 

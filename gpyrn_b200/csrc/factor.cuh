@@ -662,4 +662,24 @@ __global__ void __launch_bounds__(256) trmv_upper_norm_kernel(double* __restrict
     }
 }
 
+// Bitwise comparison of the lower triangle of matrix blockIdx.x of W (and of its log-det) with a reference factor:
+// adds 1 to *mismatches when anything differs (gprn_debug_panel_stress).  grid = (nmat), block = 256.
+__global__ void lower_mismatch_kernel(const double* __restrict__ W, const double* __restrict__ ref,
+                                      const double* __restrict__ logdet, const double* __restrict__ logdet_ref,
+                                      int Np, unsigned long long* __restrict__ mismatches) {
+    __shared__ int diff;
+    if (threadIdx.x == 0) diff = 0;
+    __syncthreads();
+    const double* Wm = W + (size_t)blockIdx.x * Np * Np;
+    int d = 0;
+    for (size_t e = threadIdx.x; e < (size_t)Np * Np; e += blockDim.x) {
+        const int r = (int)(e / Np), c = (int)(e % Np);
+        if (c <= r && __double_as_longlong(Wm[e]) != __double_as_longlong(ref[e])) d = 1;
+    }
+    if (threadIdx.x == 0 && __double_as_longlong(logdet[blockIdx.x]) != __double_as_longlong(logdet_ref[0])) d = 1;
+    if (d) diff = 1;
+    __syncthreads();
+    if (threadIdx.x == 0 && diff) atomicAdd(mismatches, 1ULL);
+}
+
 }  // namespace gprn

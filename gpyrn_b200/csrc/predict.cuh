@@ -14,12 +14,19 @@
 
 namespace gprn {
 
-// out[t] = sum_n Ks[t][n] * alpha[n].  One warp per row.  grid = (ceil(T/8)), block = 256.
-__global__ void __launch_bounds__(256) rect_gemv_kernel(double* __restrict__ out, const double* __restrict__ Ks,
-                                                        size_t ld, const double* __restrict__ alpha, int T, int N) {
+// All kernels below are batched over the GPs of one hyper-parameter set through the last grid dimension b:
+// Kstar chunk b at Ks + b*kstride, inverse factor b at X + (xid0 + b)*Np*Np, vectors / outputs with their own strides.
+
+// out[t] = sum_n Ks[t][n] * alpha[n].  One warp per row.  grid = (ceil(T/8), nb), block = 256.
+__global__ void __launch_bounds__(256) rect_gemv_kernel(double* __restrict__ out, size_t ostride,
+                                                        const double* __restrict__ Ks, size_t kstride, size_t ld,
+                                                        const double* __restrict__ alpha, size_t astride, int T, int N) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * 8 + warp;
     if (t >= T) return;
+    out += (size_t)blockIdx.y * ostride;
+    Ks += (size_t)blockIdx.y * kstride;
+    alpha += (size_t)blockIdx.y * astride;
     const double* row = Ks + (size_t)t * ld;
     double s = 0.0;
     for (int n = lane; n < N; n += 32) s = fma(row[n], alpha[n], s);
@@ -28,11 +35,14 @@ __global__ void __launch_bounds__(256) rect_gemv_kernel(double* __restrict__ out
 }
 
 // rownorm2[t] = sum_a ( sum_{n<=a} Ks[t][n] X[a][n] )^2 for the 64 test rows of this CTA.
-// Ks: [Tpad][Np] (columns >= N zero, rows >= T zero), X: [Np][Np] lower.  grid = (Tpad/64), block = 128,
+// Ks: [Tpad][Np] (columns >= N zero, rows >= T zero), X: [Np][Np] lower.  grid = (Tpad/64, nb), block = 128,
 // dynamic shared memory 2*TILE_SMEM.
-__global__ void __launch_bounds__(128) predict_norm_kernel(double* __restrict__ rownorm2,
-                                                           const double* __restrict__ Ks,
+__global__ void __launch_bounds__(128) predict_norm_kernel(double* __restrict__ rownorm2, size_t rstride,
+                                                           const double* __restrict__ Ks, size_t kstride,
                                                            const double* __restrict__ X, int Np, int N) {
+    rownorm2 += (size_t)blockIdx.y * rstride;
+    Ks += (size_t)blockIdx.y * kstride;
+    X += (size_t)blockIdx.y * Np * Np;
     extern __shared__ double smem[];
     double* As = smem;
     double* Bs = smem + NB * LDT;
@@ -78,12 +88,16 @@ __global__ void __launch_bounds__(128) predict_norm_kernel(double* __restrict__ 
 // Large-N variant of predict_norm_kernel on the DMMA GEMM core (gemm128.cuh): CTA (tt, at) forms the tile
 // C[t][a] = sum_{n <= a} Ks[t][n] X[a][n] for G_BM test epochs x 128 rows of X (K = a0 + 128, X lower triangular),
 // squares it and writes the 128 row sums to partial[at][t]; predict_var_kernel adds the partials in tile order.
-// Ks: [Tpad][Np] with zero padding (columns >= N, rows >= T).  grid = (Tpad/G_BM, Np/128), block = G_THREADS,
+// Ks: [Tpad][Np] with zero padding (columns >= N, rows >= T).  grid = (Tpad/G_BM, Np/128, nb), block = G_THREADS,
 // dynamic smem GEMM128_SMEM.  blockIdx.y is mapped to descending a so that the long-K tiles start first.
-__global__ void __launch_bounds__(G_THREADS, G_MINB) predict_norm128_kernel(double* __restrict__ partial, int Tpad,
-                                                                    const double* __restrict__ Ks,
-                                                                    const double* __restrict__ X, int Np) {
+__global__ void __launch_bounds__(G_THREADS, G_MINB) predict_norm128_kernel(double* __restrict__ partial, size_t pstride,
+                                                                    int Tpad, const double* __restrict__ Ks,
+                                                                    size_t kstride, const double* __restrict__ X,
+                                                                    int Np) {
     extern __shared__ double smem[];
+    partial += (size_t)blockIdx.z * pstride;
+    Ks += (size_t)blockIdx.z * kstride;
+    X += (size_t)blockIdx.z * Np * Np;
     __shared__ double rs[G_WARPS_N][G_BM];
     const int na = Np / G_BN;
     const int at = na - 1 - blockIdx.y, a0 = at * G_BN, t0 = blockIdx.x * G_BM;
@@ -119,12 +133,17 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) predict_norm128_kernel(doub
 
 // var[t] = k(0) + nugget - rownorm2[t]   (diagonal of Kstarstar, _gp.py:131,136-137)
 // rownorm2: [nparts][stride] partial sums (nparts = 1 for predict_norm_kernel), added in order.
-__global__ void predict_var_kernel(double* __restrict__ var, const double* __restrict__ rownorm2, int nparts,
-                                   int stride, int T, const int32_t* __restrict__ tok, int ntok,
-                                   const double* __restrict__ par, double nugget) {
+// grid = (ceil(T/256), nb); GP b uses program tok[b*GPRN_MAX_PROG..], len[b], parameters hyper + paroff[b].
+__global__ void predict_var_kernel(double* __restrict__ var, size_t vstride, const double* __restrict__ rownorm2,
+                                   size_t rstride, int nparts, int stride, int T, const int32_t* __restrict__ tok,
+                                   const int32_t* __restrict__ len, const double* __restrict__ hyper,
+                                   const int32_t* __restrict__ paroff, double nugget) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
-    double k0 = eval_prog(tok, ntok, par, 0.0, true, false) + nugget;
+    const int b = blockIdx.y;
+    var += (size_t)b * vstride;
+    rownorm2 += (size_t)b * rstride;
+    double k0 = eval_prog(tok + (size_t)b * GPRN_MAX_PROG, len[b], hyper + paroff[b], 0.0, true, false) + nugget;
     double s = 0.0;
     for (int a = 0; a < nparts; a++) s += rownorm2[(size_t)a * stride + t];
     var[t] = k0 - s;

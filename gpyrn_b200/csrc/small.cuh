@@ -17,7 +17,11 @@ namespace gprn {
 #define SMALL_MAX_NT 4
 #define SMALL_TILES 10
 #define SMALL_LDV 129              // odd strides: the fused kernel keeps the thread-per-vector substitution
+#ifdef GPRN_POTRF_V1
 #define SMALL_LDP 65               // (measured: the DMMA variant is 11 % slower here, 2 CTAs/SM already hide its latency)
+#else
+#define SMALL_LDP LDT              // potrf64 v2 works in place on the LDT layout
+#endif
 #define SMALL_SCRATCH_DOUBLES (SMALL_TILES * NB * NB)
 // 3 operand tiles + col(128) + pivs(64) + rd(64) + gacc(256) + zacc(256) + vloc(256)
 #define SMALL_SMEM ((3 * NB * LDT + 4 * NB + 3 * SMALL_MAX_NT * NB) * sizeof(double))

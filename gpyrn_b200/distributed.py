@@ -1,12 +1,52 @@
 """Sharding of independent ELBO evaluations over the GPUs of one box.
 
 The path has no data-path exchange: every hyper-parameter set is an independent ``ELBOcalc``
-(SURVEY.md 8e), the data (time, y, yerr) is replicated.  Rank r of G evaluates a contiguous or
-strided block of the B sets on its own GPU; the only collective is one all-gather of the B ELBO
-values (+ iteration counts) -- NCCL over NVLink when the ranks hold GPUs, gloo in the CPU tests of
-the partitioning logic.
+(SURVEY.md 8e), the data (time, y, yerr) is replicated.  Two ways to split a pool of B sets over G ranks:
+
+* dynamic (``elbo_pool_sharded``, the default of the benchmark): every rank keeps ``slots`` evaluations in flight on
+  its GPU and takes the next set from ONE shared counter whenever a slot frees up (``SharedCounter``: an atomic
+  fetch-add on the process group's rendezvous store -- no NCCL, no recorded costs).  Sets differ several-fold in
+  iteration count, so this is what keeps the GPUs equally busy (the reference's pattern is a process pool over
+  independent walkers, gpyrn/examples/example_4.py:66-68);
+* static (``elbo_batch_sharded``): rank r evaluates a contiguous or strided block.
+
+Either way the only collective is the reduction / gather of the B ELBO values (+ iteration counts) at the end -- NCCL
+over NVLink when the ranks hold GPUs, gloo in the CPU tests of the partitioning logic.
 """
+import itertools
+
 import numpy as np
+
+_pool_serial = itertools.count()
+
+
+class SharedCounter:
+    """Atomic work counter shared by all ranks of the process group: ``next()`` returns 0, 1, 2, ... exactly once
+    across the whole group and -1 once ``total`` has been handed out.  Backed by ``store.add`` of the rendezvous
+    store (TCPStore), which is an atomic fetch-add served by rank 0; a plain local counter without a process group."""
+
+    def __init__(self, total, key, store=None):
+        import torch.distributed as dist
+        self.total = int(total)
+        self.key = f"gprn_pool/{key}"
+        self.store = store
+        self.local = 0
+        self.handed = []
+        if store is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.store = dist.distributed_c10d._get_default_store()
+
+    def next(self):
+        if self.store is None:
+            i = self.local
+            self.local += 1
+        else:
+            i = self.store.add(self.key, 1) - 1
+        if i >= self.total:
+            return -1
+        self.handed.append(i)
+        return i
+
+    __call__ = next
 
 
 def shard_indices(B, world_size, rank, mode="strided"):
@@ -113,6 +153,57 @@ def gather_results(local_idx, local_vals, B, group=None, device=None):
             full[ids[ok]] = vals.cpu().numpy()[ok].astype(v.dtype)
         out[k] = full
     return out
+
+
+def reduce_disjoint(arrays, group=None):
+    """Combine per-rank result arrays whose supports are disjoint (every set was evaluated by exactly one rank, the
+    others hold zeros): one all-reduce(SUM) per array -- the one collective of the path.  Accepts torch tensors
+    (reduced in place, on their device) or numpy arrays (staged through the backend's device); returns the inputs'
+    kind.  No-op without a process group."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return arrays
+    backend = dist.get_backend(group)
+    out = []
+    for a in arrays:
+        if isinstance(a, torch.Tensor):
+            dist.all_reduce(a, op=dist.ReduceOp.SUM, group=group)
+            out.append(a)
+        else:
+            dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+            t = torch.as_tensor(np.ascontiguousarray(a)).to(dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            out.append(t.cpu().numpy().astype(np.asarray(a).dtype))
+    return out
+
+
+def elbo_pool_sharded(gprn, parameters, max_iter=None, slots=0, key=None, group=None, evaluate=None):
+    """Evaluate B hyper-parameter sets across all ranks with DYNAMIC dealing: every rank pulls the next set from a
+    shared counter whenever one of its ``slots`` workspace slots frees up, then one all-reduce combines the results.
+    Every rank returns the full (elbo[B], iters[B], status[B], owner[B]) -- ``owner`` is the rank that evaluated a set.
+
+    ``gprn`` is this rank's ``inference`` bound to its GPU; every rank must pass the same ``parameters`` and call this
+    the same number of times (``key`` names the counter of this call; default: a per-process call serial).
+    ``evaluate(P, work_source)`` -> (elbo, iters, status, taken) replaces ``gprn.ELBO_batch`` in the CPU tests."""
+    import torch.distributed as dist
+
+    P = np.atleast_2d(np.asarray(parameters, dtype=float))
+    B = P.shape[0]
+    rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+    counter = SharedCounter(B, next(_pool_serial) if key is None else key)
+    if evaluate is None:
+        elbo, iters, status, taken = gprn.ELBO_batch(P, max_iter=max_iter, return_info=True, slots=slots,
+                                                     work_source=counter)
+    else:
+        elbo, iters, status, taken = evaluate(P, counter)
+    taken = np.asarray(taken, dtype=bool)
+    elbo = np.where(taken, elbo, 0.0)
+    owner = np.where(taken, rank + 1, 0).astype(np.int64)
+    elbo, iters, status, owner = reduce_disjoint([elbo, np.where(taken, iters, 0).astype(np.int64),
+                                                  np.where(taken, status, 0).astype(np.int64), owner], group=group)
+    return elbo, iters, status, owner - 1
 
 
 def elbo_batch_sharded(gprn, parameters, max_iter=None, mode="strided", group=None):

@@ -9,9 +9,13 @@ only keeps the Python objects, evaluates the mean functions (O(pN), host by desi
 small arrays.  There is no CPU fallback.
 
 Additions over the reference: ``ELBO_batch(parameters[B, n])`` evaluates B hyper-parameter sets in one
-device call (the data-parallel entry used for sweeps / MCMC walkers), and ``device=`` selects the GPU.
+device call (the data-parallel entry used for sweeps / MCMC walkers) with an optional device-resident per-chain
+warm-start state, ``optimize_batch`` runs many Nelder-Mead starts in lock-step on top of it, ``logposterior_batch`` is
+the vectorised log-posterior for ensemble samplers, ``Prediction_batch`` predicts for a chain of hyper-parameter sets,
+and ``device=`` selects the GPU.
 """
 import ctypes
+import threading
 import time as time_module
 from itertools import chain
 
@@ -76,6 +80,7 @@ class inference:
             _lib.lib().gprn_destroy(self._handle)
             self._handle = None
             self._model_sig = None
+            self._n_chains = 0
 
     def __del__(self):
         try:
@@ -422,68 +427,151 @@ class inference:
         elbo, mu_out, var_out, _, _ = self._run_elbo(nodes, weights, means, jitters, 1, mu, var)
         return elbo, mu_out, var_out, None, None
 
-    def ELBO_batch(self, parameters, max_iter=None, return_info=False, mu=None, var=None, return_state=False):
+    def _full_parameter_matrix(self, parameters):
+        """(B, n_parameters) matrix from rows holding all parameters or only the free ones (the rule of
+        ``set_parameters``: frozen entries keep their current values either way)."""
+        P = np.atleast_2d(np.asarray(parameters, dtype=float))
+        n_all = self.n_parameters
+        frozen = self.frozen_mask
+        n_free = n_all - int(frozen.sum())
+        current = self.get_parameters(include_frozen=True)
+        if P.shape[1] == n_all:
+            full = P.copy()
+            full[:, frozen] = current[frozen]
+        elif P.shape[1] == n_free:
+            full = np.tile(current, (P.shape[0], 1))
+            full[:, ~frozen] = P
+        else:
+            msg = f'Wrong number of parameters provided: got {P.shape[1]}, '
+            msg += f'expected {n_all}' if n_all == n_free else f'expected {n_all} (all) or {n_free} (not frozen)'
+            raise ValueError(msg)
+        return full
+
+    def _split_parameter_matrix(self, P):
+        """Full parameter rows -> (hyper [B,H] = kernel parameters + jitters, y - mean [p*N] or [B,p*N], shared flag)."""
+        B = P.shape[0]
+        n_kernel = sum(k.pars.size for k in chain(self.nodes, self.weights))
+        n_mean = sum(m.pars.size for m in self.means if isinstance(m, meanfunc.meanFunction))
+        hyper = _lib.f64(np.concatenate([P[:, :n_kernel], P[:, n_kernel + n_mean:]], axis=1))
+        saved = [m.pars.copy() if isinstance(m, meanfunc.meanFunction) else None for m in self.means]
+        try:
+            if n_mean == 0 or np.all(P[:, n_kernel:n_kernel + n_mean] == P[0, n_kernel:n_kernel + n_mean]):
+                self._assign_means(P[0, n_kernel:n_kernel + n_mean])
+                ysub = _lib.f64(np.concatenate(self.y) - self._mean(self.means))
+                shared = 1
+            else:
+                ysub = np.empty((B, self.p * self.N))
+                for b in range(B):
+                    self._assign_means(P[b, n_kernel:n_kernel + n_mean])
+                    ysub[b] = np.concatenate(self.y) - self._mean(self.means)
+                ysub = _lib.f64(ysub)
+                shared = 0
+        finally:
+            self._restore_means(saved)
+        return hyper, ysub, shared
+
+    def ELBO_batch(self, parameters, max_iter=None, return_info=False, mu=None, var=None, return_state=False,
+                   state=None, slots=0, work_source=None):
         """
-        ELBO of B hyper-parameter sets in one device call.
+        ELBO of B hyper-parameter sets in one device call (continuous batching over the GPU's workspace slots).
 
         Args:
             parameters: array (B, n_parameters) or (B, number of free parameters), ``get_parameters`` order
             max_iter: per-evaluation iteration cap (default 10000)
             return_info: also return (iterations, status) arrays
-            mu, var: optional per-set initial variational state, arrays (B, d) -- the batched form of
-                ``ELBOcalc(mu='previous')`` for chains / walkers that carry their own state; default 'init'
-            return_state: also return the final (mu, var), arrays (B, d), to be fed back on the next call
+            mu, var: optional per-set initial variational state, host arrays (B, d); default 'init'
+            return_state: also return the final (mu, var), host arrays (B, d)
+            state: ``'previous'`` keeps one variational state per row ON THE DEVICE between calls (row b <-> chain
+                b): an evaluation starts from its chain's last converged state, or from 'init' when there is none,
+                and stores its own state when it converges -- the batched form of ``nELBO``'s warm start
+                (reference :598-607, :643-646), without moving B*d doubles per call.  ``'previous-always'`` stores
+                the state whether or not the evaluation converged.  ``reset_chain_state()`` forgets all chains.
+            slots: evaluations kept in flight (0: as many as fit the device workspace)
+            work_source: optional callable returning the next row index to evaluate, or -1 when none is left
+                (several processes sharing one counter split the rows dynamically; see
+                ``gpyrn_b200.distributed``).  Rows not handed out by it are not evaluated: their outputs are 0 and
+                the extra return value ``taken`` (bool, (B,)) is False.
 
         Returns:
-            elbo (B,) [, iterations (B,), status (B,)] [, mu (B, d), var (B, d)]
+            elbo (B,) [, iterations (B,), status (B,)] [, mu (B, d), var (B, d)] [, taken (B,)]
         """
         self._require_components()
-        P = np.atleast_2d(np.asarray(parameters, dtype=float))
+        P = self._full_parameter_matrix(parameters)
         B = P.shape[0]
-        n_all = self.n_parameters
-        if P.shape[1] != n_all:
-            full = np.tile(self.get_parameters(include_frozen=True), (B, 1))
-            full[:, ~self.frozen_mask] = P
-            P = full
-        n_kernel = sum(k.pars.size for k in chain(self.nodes, self.weights))
-        n_mean = sum(m.pars.size for m in self.means if isinstance(m, meanfunc.meanFunction))
         self._bind_model(self.nodes, self.weights)
-        hyper = _lib.f64(np.concatenate([P[:, :n_kernel], P[:, n_kernel + n_mean:]], axis=1))
-        if n_mean == 0 or np.all(P[:, n_kernel:n_kernel + n_mean] == P[0, n_kernel:n_kernel + n_mean]):
-            saved = [m.pars.copy() if isinstance(m, meanfunc.meanFunction) else None for m in self.means]
-            self._assign_means(P[0, n_kernel:n_kernel + n_mean])
-            ysub = _lib.f64(np.concatenate(self.y) - self._mean(self.means))
-            self._restore_means(saved)
-            shared = 1
-        else:
-            saved = [m.pars.copy() if isinstance(m, meanfunc.meanFunction) else None for m in self.means]
-            ysub = np.empty((B, self.p * self.N))
-            for b in range(B):
-                self._assign_means(P[b, n_kernel:n_kernel + n_mean])
-                ysub[b] = np.concatenate(self.y) - self._mean(self.means)
-            self._restore_means(saved)
-            ysub = _lib.f64(ysub)
-            shared = 0
+        hyper, ysub, shared = self._split_parameter_matrix(P)
         elbo = np.empty(B)
         iters = np.zeros(B, dtype=np.int32)
         status = np.zeros(B, dtype=np.int32)
-        init_mode, mu_io, var_io = 0, None, None
-        if mu is not None or var is not None:
-            if mu is None or var is None:
-                raise ValueError('provide both mu and var, or neither')
-            mu_io = _lib.f64(np.array(mu, dtype=float).reshape(B, self.d))
-            var_io = _lib.f64(np.array(var, dtype=float).reshape(B, self.d))
-            init_mode = 1
-        elif return_state:
-            mu_io, var_io = np.empty((B, self.d)), np.empty((B, self.d))
-        _lib.check(_lib.lib().gprn_elbo_batched(self._h(), B, _lib.dptr(hyper), _lib.dptr(ysub), shared, init_mode,
-                                                _lib.dptr(mu_io), _lib.dptr(var_io),
-                                                -1 if max_iter is None else max_iter, _lib.dptr(elbo),
-                                                _lib.iptr(iters), _lib.iptr(status), None))
+        L = _lib.lib()
+        mi = -1 if max_iter is None else max_iter
+        if state is None and work_source is None and not slots:
+            init_mode, mu_io, var_io = 0, None, None
+            if mu is not None or var is not None:
+                if mu is None or var is None:
+                    raise ValueError('provide both mu and var, or neither')
+                mu_io = _lib.f64(np.array(mu, dtype=float).reshape(B, self.d))
+                var_io = _lib.f64(np.array(var, dtype=float).reshape(B, self.d))
+                init_mode = 1
+            elif return_state:
+                mu_io, var_io = np.empty((B, self.d)), np.empty((B, self.d))
+            _lib.check(L.gprn_elbo_batched(self._h(), B, _lib.dptr(hyper), _lib.dptr(ysub), shared, init_mode,
+                                           _lib.dptr(mu_io), _lib.dptr(var_io), mi, _lib.dptr(elbo),
+                                           _lib.iptr(iters), _lib.iptr(status), None))
+            out = (elbo, iters, status) if return_info else (elbo,)
+            if return_state:
+                out = out + (mu_io, var_io)
+            return out if len(out) > 1 else out[0]
+        # pool entry: device-resident chain state and / or an external work source
+        if state not in (None, 'previous', 'previous-always'):
+            raise ValueError("state must be None, 'previous' or 'previous-always'")
+        if (mu is None) != (var is None):
+            raise ValueError('provide both mu and var, or neither')
+        state_mode = {None: 0, 'previous': 1, 'previous-always': 2}[state]
+        if state_mode == 0 and (mu is not None or return_state):
+            state_mode = 2                          # host state in / out goes through the store as well
+            self.reset_chain_state()
+        if state_mode:
+            self._ensure_chain_state(B)
+            if mu is not None:
+                _lib.check(L.gprn_chain_set(self._h(), 0, B, _lib.dptr(_lib.f64(np.array(mu).reshape(B, self.d))),
+                                            _lib.dptr(_lib.f64(np.array(var).reshape(B, self.d)))))
+        taken = np.zeros(B, dtype=np.int32)
+        cb = None
+        if work_source is not None:
+            cb = _lib.NEXT_SET_FN(lambda _user: int(work_source()))
+        _lib.check(L.gprn_elbo_pool(self._h(), B, hyper.ctypes.data, 0, _lib.dptr(ysub), shared,
+                                    ctypes.cast(cb, ctypes.c_void_p) if cb is not None else None, None, int(slots),
+                                    state_mode, mi, elbo.ctypes.data, iters.ctypes.data, status.ctypes.data,
+                                    taken.ctypes.data, 0, None))
         out = (elbo, iters, status) if return_info else (elbo,)
         if return_state:
-            out = out + (mu_io, var_io)
+            mu_o, var_o = np.empty((B, self.d)), np.empty((B, self.d))
+            _lib.check(L.gprn_chain_get(self._h(), 0, B, _lib.dptr(mu_o), _lib.dptr(var_o), None))
+            out = out + (mu_o, var_o)
+        if work_source is not None:
+            out = out + (taken.astype(bool),)
         return out if len(out) > 1 else out[0]
+
+    def _ensure_chain_state(self, B):
+        if getattr(self, '_n_chains', 0) != B:
+            _lib.check(_lib.lib().gprn_chain_resize(self._h(), B))
+            self._n_chains = B
+
+    def reset_chain_state(self):
+        """Forget the device-resident per-chain variational states: the next ``ELBO_batch(state='previous')``
+        starts every row from 'init'."""
+        if getattr(self, '_n_chains', 0):
+            _lib.check(_lib.lib().gprn_chain_invalidate(self._h(), 0, self._n_chains))
+
+    def get_chain_state(self):
+        """Host copy of the device-resident chain states: mu (B, d), var (B, d), valid (B,) bool."""
+        B = getattr(self, '_n_chains', 0)
+        if not B:
+            raise ValueError("no chain state: call ELBO_batch(..., state='previous') first")
+        mu, var, valid = np.empty((B, self.d)), np.empty((B, self.d)), np.zeros(B, dtype=np.int32)
+        _lib.check(_lib.lib().gprn_chain_get(self._h(), 0, B, _lib.dptr(mu), _lib.dptr(var), _lib.iptr(valid)))
+        return mu, var, valid.astype(bool)
 
     def _assign_means(self, values):
         rest = np.asarray(values, dtype=float)
@@ -536,6 +624,130 @@ class inference:
         self.set_parameters(res.x)
         return res
 
+    def nELBO_batch(self, parameters, max_iter=None):
+        """Negative ELBO of B parameter rows, each warm-started from its own chain's last converged state kept on the
+        device (row b <-> chain b): the batched ``nELBO`` (reference :1095-1111).  The object's own parameters are
+        left untouched."""
+        return -self.ELBO_batch(parameters, max_iter=max_iter, state='previous')
+
+    def optimize_batch(self, starts, vars=None, max_iter=None, **kwargs):
+        """
+        Multi-start optimisation: S independent ``scipy.optimize.minimize`` runs (Nelder-Mead by default, exactly the
+        driver of ``optimize``, reference :1114-1152) advanced in LOCK-STEP -- every round, the one objective
+        evaluation each live start is waiting for goes to the GPU as a single ``ELBO_batch`` call, each start
+        warm-started from its own device-resident variational state (what ``nELBO``'s ``'previous'`` does for a
+        single run).  The optimiser logic is scipy's own, run as S coroutines, so a start returns what a sequential
+        ``optimize`` from the same point would.
+
+        Args:
+            starts: array (S, number of free parameters) of initial points
+            vars: as ``optimize``
+            max_iter: iteration cap of every ELBO evaluation (default 10000)
+            **kwargs: passed to ``scipy.optimize.minimize``
+
+        Returns:
+            list of S ``OptimizeResult``; the object's parameters are set to the best one.
+        """
+        from scipy.optimize import minimize
+        self._require_components()
+        self._select_vars(vars)
+        kwargs.setdefault('method', 'Nelder-Mead')
+        X0 = np.atleast_2d(np.asarray(starts, dtype=float))
+        S = X0.shape[0]
+        n_free = self.n_parameters - int(self.frozen_mask.sum())
+        if X0.shape[1] != n_free:
+            raise ValueError(f'starts must have {n_free} columns (the free parameters), got {X0.shape[1]}')
+        cond = threading.Condition()
+        request = [None] * S           # point a start is waiting on
+        value = [None] * S
+        done = [False] * S
+        results = [None] * S
+        errors = []
+        self.reset_chain_state()
+        self._ensure_chain_state(S)
+
+        def objective(s):
+            def f(x):
+                with cond:
+                    request[s] = np.array(x, dtype=float)
+                    cond.notify_all()
+                    while value[s] is None and not errors:
+                        cond.wait()
+                    if errors:
+                        raise RuntimeError('optimize_batch aborted')
+                    v, value[s] = value[s], None
+                return v
+            return f
+
+        def run(s):
+            try:
+                results[s] = minimize(objective(s), X0[s], **kwargs)
+            except BaseException as e:          # noqa: BLE001 - reported by the coordinator
+                with cond:
+                    errors.append(e)
+            finally:
+                with cond:
+                    done[s] = True
+                    cond.notify_all()
+
+        threads = [threading.Thread(target=run, args=(s,), daemon=True) for s in range(S)]
+        for t in threads:
+            t.start()
+        P = np.tile(X0[0], (S, 1))
+        self.n_batch_calls = 0
+        try:
+            while True:
+                with cond:
+                    while not errors and not all(done[s] or request[s] is not None for s in range(S)):
+                        cond.wait()
+                    if errors or all(done):
+                        break
+                    live = [s for s in range(S) if request[s] is not None]
+                    for s in live:
+                        P[s] = request[s]
+                        request[s] = None
+                it = iter(live)
+                elbo, taken = self.ELBO_batch(P, max_iter=max_iter, state='previous',
+                                              work_source=lambda: next(it, -1))
+                self.n_batch_calls += 1
+                with cond:
+                    for s in live:
+                        value[s] = -float(elbo[s])
+                    cond.notify_all()
+        except BaseException as e:              # noqa: BLE001
+            with cond:
+                errors.append(e)
+                cond.notify_all()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        best = min(range(S), key=lambda s: results[s].fun if np.isfinite(results[s].fun) else np.inf)
+        self.set_parameters(results[best].x)
+        return results
+
+    def logposterior_batch(self, thetas, priors, names=None, max_iter=100):
+        """Vectorised log-posterior for ensemble samplers (emcee ``vectorize=True``): rows of ``thetas`` are walker
+        positions in the free parameters; returns (log prior + ELBO, ELBO), each (B,).  One ``ELBO_batch`` call for
+        the rows with a finite prior, capped at ``max_iter`` iterations like the reference's ``logposterior``
+        (:1214-1219), warm-started per row from the device-resident chain state."""
+        self._require_components()
+        thetas = np.atleast_2d(np.asarray(thetas, dtype=float))
+        if names is None:
+            names = np.array(list(self.parameters_dict.keys()))[~self.frozen_mask]
+        lp = np.array([sum(priors[n].logpdf(v) for v, n in zip(row, names)) for row in thetas], dtype=float)
+        ok = np.isfinite(lp)
+        elbo = np.full(thetas.shape[0], -np.inf)
+        if ok.any():
+            live = np.flatnonzero(ok)
+            it = iter(live.tolist())
+            # rows outside the prior support are never handed out; give them a harmless in-support stand-in
+            rows = np.where(ok[:, None], thetas, thetas[live[0]])
+            e, _ = self.ELBO_batch(rows, max_iter=max_iter, state='previous', work_source=lambda: next(it, -1))
+            elbo[live] = e[live]
+        total = np.where(ok, lp + elbo, -np.inf)
+        return total, elbo
+
     def mcmc(self, priors, p0=None, vars=None, niter=500, **kwargs):
         """Posterior sampling of the hyper-parameters with emcee (the sampler itself is a host driver
         outside this package's scope; it needs the optional ``emcee`` dependency)."""
@@ -547,21 +759,16 @@ class inference:
         self._select_vars(vars)
         names = np.array(list(self.parameters_dict.keys()))[~self.frozen_mask]
 
-        def logprior(theta):
-            return sum(priors[n].logpdf(v) for v, n in zip(theta, names))
-
-        def logposterior(theta):
-            lp = logprior(theta)
-            if np.isneginf(lp):
-                return -np.inf, -np.inf
-            elbo = -self.nELBO(theta, max_iter=100)
-            return lp + elbo, elbo
+        def logposterior(thetas):                 # emcee vectorize=True: (walkers in the move, ndim) -> blobs
+            total, elbo = self.logposterior_batch(thetas, priors, names=names, max_iter=100)
+            return np.column_stack([total, elbo])
 
         ndim = len(names)
         nwalkers = 2 * ndim
         if p0 is None:
             p0 = np.array([[priors[n].rvs() for n in names] for _ in range(nwalkers)])
-        sampler = EnsembleSampler(nwalkers, ndim, logposterior, **kwargs)
+        self.reset_chain_state()
+        sampler = EnsembleSampler(nwalkers, ndim, logposterior, vectorize=True, **kwargs)
         sampler.run_mcmc(p0, niter, progress=False)
         return sampler
 
@@ -621,30 +828,32 @@ class inference:
             mean (B, T, p), variance (B, T, p) [, elbo (B,), iterations (B,), status (B,)]
         """
         self._require_components()
-        P = np.atleast_2d(np.asarray(parameters, dtype=float))
+        P = self._full_parameter_matrix(parameters)
         B = P.shape[0]
-        if P.shape[1] != self.n_parameters:
-            full = np.tile(self.get_parameters(include_frozen=True), (B, 1))
-            full[:, ~self.frozen_mask] = P
-            P = full
         tstar = self.time if tstar is None else np.atleast_1d(np.asarray(tstar, dtype=float))
         elbo, iters, status, mu, var = self.ELBO_batch(P, max_iter=max_iter, return_info=True, return_state=True)
         n_kernel = sum(k.pars.size for k in chain(self.nodes, self.weights))
         n_mean = sum(m.pars.size for m in self.means if isinstance(m, meanfunc.meanFunction))
         T = tstar.size
         ts = _lib.f64(tstar)
-        pm, pv = np.empty((B, T, self.p)), np.empty((B, T, self.p))
+        hyper = _lib.f64(np.concatenate([P[:, :n_kernel], P[:, n_kernel + n_mean:]], axis=1))
         saved = [m.pars.copy() if isinstance(m, meanfunc.meanFunction) else None for m in self.means]
         try:
-            for b in range(B):
-                self._assign_means(P[b, n_kernel:n_kernel + n_mean])
-                mean_t = _lib.f64(self._mean(self.means, tstar))
-                hyper = _lib.f64(np.concatenate([P[b, :n_kernel], P[b, n_kernel + n_mean:]]))
-                _lib.check(_lib.lib().gprn_predict(self._h(), _lib.dptr(hyper), _lib.dptr(_lib.f64(mu[b])),
-                                                   _lib.dptr(_lib.f64(var[b])), _lib.dptr(ts), T, _lib.dptr(mean_t),
-                                                   _lib.dptr(pm[b]), _lib.dptr(pv[b]), None, None, None))
+            if n_mean == 0 or np.all(P[:, n_kernel:n_kernel + n_mean] == P[0, n_kernel:n_kernel + n_mean]):
+                self._assign_means(P[0, n_kernel:n_kernel + n_mean])
+                mean_t, shared = _lib.f64(self._mean(self.means, tstar)), 1
+            else:
+                mean_t, shared = np.empty((B, self.p * T)), 0
+                for b in range(B):
+                    self._assign_means(P[b, n_kernel:n_kernel + n_mean])
+                    mean_t[b] = self._mean(self.means, tstar)
         finally:
             self._restore_means(saved)
+        pm, pv = np.empty((B, T, self.p)), np.empty((B, T, self.p))
+        # one device call: assembly / factorisation / solves batched over the GPs of all sets that fit the workspace
+        _lib.check(_lib.lib().gprn_predict_batched(self._h(), B, _lib.dptr(hyper), _lib.dptr(_lib.f64(mu)),
+                                                   _lib.dptr(_lib.f64(var)), _lib.dptr(ts), T, _lib.dptr(mean_t), shared,
+                                                   _lib.dptr(pm), _lib.dptr(pv), None, None, None))
         if return_info:
             return pm, pv, elbo, iters, status
         return pm, pv

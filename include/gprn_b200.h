@@ -73,6 +73,8 @@ int gprn_destroy(gprn_handle* h);
 
 /* Optional cap (bytes) on the device workspace used by gprn_elbo_batched (0 = automatic). */
 int gprn_set_workspace_limit(gprn_handle* h, uint64_t bytes);
+/* Optional cap on the number of evaluations kept in flight by the batched entry points (0 = as many as fit). */
+int gprn_set_max_slots(gprn_handle* h, int slots);
 
 /* Model structure: replaces the kernel objects held by inference.set_components
  * (gpyrn/meanfield.py:136-178).  Programs are concatenated; node_prog_off has q+1 entries,
@@ -104,6 +106,38 @@ int gprn_upload_ysub(gprn_handle* h, const double* ysub /* p*N, shared by all se
 int gprn_elbo_batched_dev(gprn_handle* h, int B, const double* d_hyper, int max_iter, double* d_elbo_out,
                           int32_t* d_iters_out, int32_t* d_status_out, void* stream);
 
+/* Pool form of the batched evaluation: the data-parallel entry for sweeps, multi-start optimisation and MCMC
+ * walkers (the reference's pattern is a process pool over independent walkers, gpyrn/examples/example_4.py:66-68,
+ * each calling inference.nELBO / logposterior, gpyrn/meanfield.py:1095-1111, 1214-1219).
+ *   hyper      [B*n_hyper]  the whole pool, host or (hyper_on_device != 0) device memory
+ *   ysub       as gprn_elbo_batched (host), or NULL: keep what gprn_upload_ysub / the last call left on the device
+ *   next,user  work source: called from the calling thread, returns the next pool index to evaluate or -1 when
+ *              the pool is exhausted.  NULL: every set 0..B-1 in order.  Several processes (one per GPU) that
+ *              share one counter split a pool dynamically: each takes a new set whenever one of its slots frees up.
+ *   max_slots  evaluations kept in flight on this GPU (0: the handle's default, see gprn_set_max_slots).  A set
+ *              that converges is retired and its slot refilled from the work source in the next lock-step round
+ *              (continuous batching).
+ *   state_mode 0: every evaluation starts from _initMuVar ('init').
+ *              1: chain-state store ('previous', meanfield.py:598-607): set b starts from chain b when that entry is
+ *                 valid and from 'init' otherwise; the final state is written back when the evaluation converged
+ *                 (the reference caches self._mu / self._var only then, :643-646).
+ *              2: as 1, but the final state is always written back.
+ *   outputs    [B] each, host or (out_on_device != 0) device; entries of sets this call did not evaluate are zero
+ *              and taken_out (may be NULL) is 1 exactly for the sets it did evaluate. */
+typedef int64_t (*gprn_next_set_fn)(void* user);
+int gprn_elbo_pool(gprn_handle* h, int64_t B, const double* hyper, int hyper_on_device, const double* ysub,
+                   int ysub_shared, gprn_next_set_fn next, void* user, int max_slots, int state_mode, int max_iter,
+                   double* elbo_out, int32_t* iters_out, int32_t* status_out, int32_t* taken_out, int out_on_device,
+                   void* stream);
+
+/* Device-resident variational state of n chains, d doubles each for mu and var: the batched form of the reference's
+ * self._mu / self._var cache (gpyrn/meanfield.py:112-113, 598-607, 643-646).  resize invalidates every entry;
+ * set uploads host state and marks it valid; get downloads (any of mu / var / valid may be NULL). */
+int gprn_chain_resize(gprn_handle* h, int64_t n);
+int gprn_chain_set(gprn_handle* h, int64_t first, int64_t n, const double* mu, const double* var);
+int gprn_chain_get(gprn_handle* h, int64_t first, int64_t n, double* mu, double* var, int32_t* valid);
+int gprn_chain_invalidate(gprn_handle* h, int64_t first, int64_t n);
+
 /* Covariance-matrix assembly: replaces inference._KMatrix (gpyrn/meanfield.py:413-434),
  * _gp.GP._kernel_matrix / _predict_kernel_matrix (gpyrn/_gp.py:40-62).
  * K_out[n_rows*n_cols] host, row-major.  t_cols == NULL means the square case k(t_rows - t_rows^T)
@@ -116,6 +150,7 @@ int gprn_kmatrix(gprn_handle* h, const int32_t* prog, int prog_len, const double
 /* Element-wise kernel evaluation out[i][j] = k(r[i][j]) on an arbitrary lag array (host in, host out):
  * replaces covFunction.__call__(r) (gpyrn/covfunc.py, same lines as the opcode table above) for the
  * host-side kernel objects.  `square` != 0 applies the WhiteNoise identity-by-position rule. */
+/* device < 0: the calling thread's current CUDA device. */
 int gprn_keval(int device, const int32_t* prog, int prog_len, const double* pars, int n_pars, const double* r,
                int64_t n_rows, int64_t n_cols, int square, double* out);
 
@@ -135,9 +170,21 @@ int gprn_predict(gprn_handle* h, const double* hyper, const double* mu, const do
                  const double* tstar, int T, const double* mean_at_tstar, double* pred_mean,
                  double* pred_var, double* node_pred, double* weight_pred, void* stream);
 
+/* The same for B hyper-parameter sets (a posterior chain): hyper[B*n_hyper], mu / var [B*d]; mean_at_tstar is
+ * [p*T] shared by all sets (mean_shared != 0) or [B*p*T]; outputs [B][T][p], node_pred [B][q][T],
+ * weight_pred [B][q*p][T].  Assembly, factorisation and the A^-1 m solves are batched over all GPs of as many
+ * sets as fit the workspace. */
+int gprn_predict_batched(gprn_handle* h, int B, const double* hyper, const double* mu, const double* var,
+                         const double* tstar, int T, const double* mean_at_tstar, int mean_shared,
+                         double* pred_mean, double* pred_var, double* node_pred, double* weight_pred, void* stream);
+
 /* Test hook for the factorisation kernels: A[n*n] host SPD (row-major) -> L = chol(A) (lower),
  * X = L^-1 (lower), logdet(A).  Either output may be NULL. */
 int gprn_debug_factor(gprn_handle* h, int n, const double* A, double* L_out, double* X_out, double* logdet_out);
+
+/* Stress self-check of the one-launch panel step (last-reader ticket): nmat copies of A are factored reps times
+ * and compared bit for bit with the two-launch path; *mismatches_out counts differing (repetition, matrix) pairs. */
+int gprn_debug_panel_stress(gprn_handle* h, int n, const double* A, int nmat, int reps, int64_t* mismatches_out);
 
 /* Counters: kernels launched by this handle since creation / last reset, and device time of the
  * last gprn_elbo_batched* call in milliseconds (CUDA events on the launching stream). */
@@ -146,6 +193,10 @@ int gprn_reset_launch_count(gprn_handle* h);
 double gprn_last_elbo_ms(gprn_handle* h);
 /* Sum over the evaluations of the last batched call of the iteration counts (for flop accounting). */
 int64_t gprn_last_total_iters(gprn_handle* h);
+/* CUDA-graph replays (one per lock-step iteration when no slot is being refilled) since the last reset; the
+ * kernels inside them are included in gprn_launch_count.  Lock-step rounds of the last batched call. */
+int64_t gprn_graph_launch_count(gprn_handle* h);
+int64_t gprn_last_rounds(gprn_handle* h);
 
 #ifdef __cplusplus
 }

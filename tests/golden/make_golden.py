@@ -177,6 +177,56 @@ def big_anchors():
         print(f"{name}: ELBO={elbo!r} iters={it}", flush=True)
 
 
+def big_converged(which):
+    """Converged large-N anchors: the reference run to its own stopping rule.
+    c5:  C5-size N=2048 theta_0 + _Prediction on every 10th epoch of the T=20000 grid of SURVEY.md 8d;
+    c4a: C4 theta_0;  c4b: set 0 of the bench pool (perturbed_sets(theta_0, ., seed=102)[0]).
+    About 1 min of host time per ELBOaux at N=4096 on 8 cores: run once, in the background."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import workloads
+    N = 2048 if which == "c5" else 4096
+    a = workloads.synth_arrays(N, 4, 2, seed=1, node="M52")
+    th = workloads.theta0(a)
+    if which == "c4b":
+        th = workloads.perturbed_sets(th, 32, 102)[0]
+    nodes = [("M52", th[2 * j], th[2 * j + 1]) for j in range(2)]
+    weights = [("SE", th[4 + 2 * k], th[4 + 2 * k + 1]) for k in range(8)]
+    jit = th[-4:]
+    args = []
+    for y, e in zip(a["y"], a["yerr"]):
+        args += [y, e]
+    g = meanfield.inference(2, a["t"], *args)
+    g.set_components([build_kernel(s) for s in nodes], [build_kernel(s) for s in weights],
+                     [meanfunc.Constant(0.0)] * 4, list(jit))
+    trace = []
+    orig = g.ELBOaux
+
+    def rec(*aa, **k):
+        out = orig(*aa, **k)
+        trace.append(float(out[0]))
+        print(f"  {which} ELBOaux #{len(trace)}: {out[0]!r}", flush=True)
+        return out
+
+    g.ELBOaux = rec
+    elbo, mu, var, it = g.ELBOcalc()
+    out = dict(N=N, p=4, q=2, seed=1, node="M52", theta=th, max_iter=-1, elbo=float(elbo), iters=int(it),
+               trace=np.array(trace), mu=np.asarray(mu), var=np.asarray(var))
+    name = {"c5": "c5_synth_2048_4_2_M52_conv", "c4a": "c4_synth_4096_4_2_M52_conv",
+            "c4b": "c4_pool102_set0_4096_4_2_M52_conv"}[which]
+    np.savez_compressed(os.path.join(HERE, "big", name + ".npz"), **out)
+    print(f"{name}: ELBO={elbo!r} iters={it}", flush=True)
+    if which == "c5":
+        t = a["t"]
+        ptp = t[-1] - t[0]
+        full = np.linspace(t[0] - 0.2 * ptp, t[-1] + 0.2 * ptp, 20000)
+        sl = np.arange(0, 20000, 10)
+        pm, pv, sep = g._Prediction(tstar=full[sl], mu=np.asarray(mu), var=np.asarray(var), separate=True)
+        out.update(T_full=20000, slice_idx=sl, pred_mean=pm, pred_var=pv, node_pred=np.array(sep[0], float),
+                   weight_pred=np.array(sep[1], float))
+        np.savez_compressed(os.path.join(HERE, "big", name + ".npz"), **out)
+        print(f"{name}: prediction slice done", flush=True)
+
+
 def derivative_case():
     """Derivative kernels (covfunc.py:80-104) through the whole ELBO / prediction path."""
     t, ys, es = synth_data(60, 2, seed=11)
@@ -186,6 +236,11 @@ def derivative_case():
 
 
 def main():
+    if "--big-converged" in sys.argv:
+        os.makedirs(os.path.join(HERE, "big"), exist_ok=True)
+        for which in sys.argv[sys.argv.index("--big-converged") + 1:]:
+            big_converged(which)
+        return
     if "--big" in sys.argv:
         os.makedirs(os.path.join(HERE, "big"), exist_ok=True)
         big_anchors()

@@ -58,6 +58,22 @@ def test_balanced_assignment_with_lockstep_cost_model():
     assert max(c) / min(c) < 1.03                   # 1.12 with the iteration sums alone
 
 
+def test_shared_counter_single_process():
+    c = D.SharedCounter(3, "solo")
+    assert [c.next(), c.next(), c(), c.next(), c.next()] == [0, 1, 2, -1, -1]
+    assert c.handed == [0, 1, 2]
+    P = np.arange(12.0).reshape(4, 3)
+
+    def evaluate(PP, counter):
+        taken = np.zeros(len(PP), bool)
+        while (i := counter.next()) >= 0:
+            taken[i] = True
+        return PP.sum(axis=1), np.full(len(PP), 7, np.int32), np.zeros(len(PP), np.int32), taken
+
+    e, it, st, owner = D.elbo_pool_sharded(None, P, evaluate=evaluate)
+    assert np.allclose(e, P.sum(axis=1)) and np.all(it == 7) and np.all(owner == 0)
+
+
 def test_gather_single_process():
     idx = np.array([0, 2, 4])
     out = D.gather_results(idx, {"elbo": np.array([1.0, 2.0, 3.0])}, 5)
@@ -82,6 +98,29 @@ def _worker(rank, world, port, B, q):
     P = np.arange(B * 3, dtype=float).reshape(B, 3)
     e, it, st = D.elbo_batch_sharded(Fake(), P, mode="block")
     ok = ok and np.allclose(e, P.sum(axis=1)) and np.all(it == 5) and np.all(st == 0)
+    # dynamic dealing: both ranks pull set indices from ONE shared counter (TCPStore add), a slow and a fast rank;
+    # every set is evaluated exactly once, the all-reduce hands every rank the complete result
+    import time as _time
+
+    def evaluate(PP, counter):
+        e = np.zeros(len(PP)); it = np.zeros(len(PP), np.int32); st = np.zeros(len(PP), np.int32)
+        taken = np.zeros(len(PP), bool)
+        while True:
+            i = counter.next()
+            if i < 0:
+                break
+            _time.sleep(0.002 * (1 + 4 * rank))           # rank 1 is five times slower
+            e[i], it[i], taken[i] = PP[i].sum(), 4 + i % 3, True
+        return e, it, st, taken
+
+    e, it, st, owner = D.elbo_pool_sharded(None, P, key="t1", evaluate=evaluate)
+    ok = ok and np.allclose(e, P.sum(axis=1)) and np.array_equal(it, 4 + np.arange(B) % 3) and np.all(st == 0)
+    ok = ok and set(np.unique(owner).tolist()) <= {0, 1} and np.all(owner >= 0)
+    if B >= 32:
+        ok = ok and (owner == 0).sum() > (owner == 1).sum()       # the fast rank took more sets
+    # a second pool must start from a fresh counter
+    e2, _, _, owner2 = D.elbo_pool_sharded(None, P[::-1].copy(), key="t2", evaluate=evaluate)
+    ok = ok and np.allclose(e2, P[::-1].sum(axis=1))
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()
