@@ -57,7 +57,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    "c4": dict(N=4096, p=4, q=2, node="M52", pool_per_gpu=8, seed=102, slots=0,
+    "c4": dict(N=4096, p=4, q=2, node="M52", pool_per_gpu=12, seed=102, slots=0,
                anchor="c4_pool102_set0_4096_4_2_M52_conv",
                name="C4 synth(N=4096,p=4,q=2,Matern52 nodes, SE weights), batched ELBOcalc to convergence"),
     "c3": dict(N=256, p=4, q=1, node="QP", pool_per_gpu=8192, seed=101, slots=0, anchor=None,
@@ -288,7 +288,9 @@ def traffic_model(wname, N, iters_total, evals):
         return None
 
 
-def run_ours(args, w):
+def measure(args, w, wname, steps, warmup, e2e_cap, with_cpu, tag=""):
+    """One workload on all ranks: `warmup` untimed + `steps` timed steps with the pool resident in HBM, then the
+    end-to-end loop through the product API.  Returns the JSON-line dict on rank 0, None elsewhere."""
     import ctypes
     import torch
     import torch.distributed as dist
@@ -297,16 +299,12 @@ def run_ours(args, w):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; gpyrn_b200 has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     a, th0 = build_problem(w)
     N, p, q = w["N"], w["p"], w["q"]
     theta, base = pool_of(w, th0, world, args.scaling, args.pool)
     B, H = theta.shape
     slots = args.slots if args.slots else w["slots"]
+    first, grain = D.dealing_grains(B, world, slots)
     g = make_inference(a, w, local)
     P = np.concatenate([theta[:, :-p], np.zeros((B, p)), theta[:, -p:]], axis=1)      # get_parameters order
     L = _lib.lib()
@@ -325,7 +323,7 @@ def run_ours(args, w):
     def step_dev():
         """One step with the pool resident in HBM: dynamic dealing + the result all-reduce, all on `stream`."""
         serial[0] += 1
-        counter = D.SharedCounter(B, f"dev{serial[0]}")
+        counter = D.SharedCounter(B, f"{tag}dev{serial[0]}", first=first, grain=grain)
         cb = _lib.NEXT_SET_FN(lambda _u: counter.next())
         _lib.check(L.gprn_elbo_pool(h, B, d_hyper.data_ptr(), 1, None, 1, ctypes.cast(cb, ctypes.c_void_p), None, slots,
                                     0, -1, d_elbo.data_ptr(), d_iters.data_ptr(), d_status.data_ptr(),
@@ -339,7 +337,7 @@ def run_ours(args, w):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_dev()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -349,7 +347,7 @@ def run_ours(args, w):
     ms = 0.0
     rounds = 0
     mine = None
-    for _ in range(args.steps):
+    for _ in range(steps):
         flush.fill_(1)                                  # evict L2 between steps (outside the timed events)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -369,12 +367,12 @@ def run_ours(args, w):
     mine = mine.cpu().numpy().astype(bool)
     assert np.all(taken_all == 1), "every set of the pool must be evaluated by exactly one rank"
     # end to end through the product API (host buffers in, host results out, dynamic dealing, gather included)
-    D.elbo_pool_sharded(g, P[:max(1, min(B, 2))], slots=slots, key="e2e-warm")
+    D.elbo_pool_sharded(g, P[:max(1, min(B, 2))], slots=slots, key=f"{tag}e2e-warm")
     barrier()
-    e2e_steps = args.steps if not args.e2e_steps else min(args.steps, args.e2e_steps)
+    e2e_steps = steps if not e2e_cap else min(steps, e2e_cap)
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        e_api, it_api, st_api, owner = D.elbo_pool_sharded(g, P, slots=slots, key=f"e2e{k}")
+        e_api, it_api, st_api, owner = D.elbo_pool_sharded(g, P, slots=slots, key=f"{tag}e2e{k}")
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -398,12 +396,12 @@ def run_ours(args, w):
         ms_tot, e2e_ms = float(t_ms[0]), float(t_ms[1])
         launches_all, graphs_all = float(cnt[0]), float(cnt[1])
         peak, peak_src = fp64_peak()
-        value = B * args.steps / (ms_tot * 1e-3)
+        value = B * steps / (ms_tot * 1e-3)
         flops_step = algorithmic_flops(N, p, q, iters_all)
         flops_min = algorithmic_flops(N, p, q, iters_all, cross=2.0 / 3.0)
-        achieved = flops_step * args.steps / (ms_tot * 1e-3) / 1e12 / world      # per GPU
-        achieved_min = flops_min * args.steps / (ms_tot * 1e-3) / 1e12 / world
-        traffic = traffic_model(args.workload, N, float(iters_all.sum()), B)
+        achieved = flops_step * steps / (ms_tot * 1e-3) / 1e12 / world      # per GPU
+        achieved_min = flops_min * steps / (ms_tot * 1e-3) / 1e12 / world
+        traffic = traffic_model(wname, N, float(iters_all.sum()), B)
         anchor = None
         rec = reference_iterations(w)
         if rec:       # pool set 0 has a converged record of the unmodified reference: compare the run against it
@@ -412,16 +410,17 @@ def run_ours(args, w):
                       "source": "tests/golden/big/%s.npz (unmodified reference, converged)" % w["anchor"]}
         cfg = config_of(args, w, world)
         out = {"metric": "elbo_evals_per_sec", "value": value, "unit": "elbo_evals/s", "n_gpus": world,
-               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_tot / args.steps, "higher_is_better": True,
+               "steps": steps, "warmup": warmup, "ms_per_step": ms_tot / steps, "higher_is_better": True,
                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
                "run": {"slots_per_gpu": slots if slots else "all that fit", "mean_iterations": float(iters_all.mean()),
-                       "elbo_iterations_per_sec": float(iters_all.sum()) * args.steps / (ms_tot * 1e-3),
+                       "elbo_iterations_per_sec": float(iters_all.sum()) * steps / (ms_tot * 1e-3),
                        "not_converged_or_failed": int((status_all != 0).sum()),
-                       "dealing": "dynamic: shared counter on the rendezvous store, natural order; result all-reduce inside the timed step",
+                       "dealing": f"dynamic: shared counter on the rendezvous store, natural order, first grain {first} then {grain}; "
+                                  "result all-reduce inside the timed step",
                        "sets_per_rank_last_step": [int(x) for x in per_rank[:, 0].tolist()],
                        "iterations_per_rank_last_step": [int(x) for x in per_rank[:, 1].tolist()],
                        "device_ms_per_rank": [float(x) for x in per_rank[:, 2].tolist()],
-                       "lockstep_rounds_per_step": float(cnt[4]) / args.steps / world,
+                       "lockstep_rounds_per_step": float(cnt[4]) / steps / world,
                        "l2": "256 MiB flush between steps; per-step working set (K, L, L^-1 per matrix) >> 126 MB L2"
                              if N >= 1024 or B > 64 else "256 MiB flush between steps",
                        "elbo_checksum": float(np.sum(elbo_all)), "anchor": anchor},
@@ -434,9 +433,9 @@ def run_ours(args, w):
                             "what": "whole batched evaluation, algorithmic FP64 flops (SURVEY.md 8d) / device time, per GPU; "
                                     "frac_executed_min counts the cross-node trace at (2/3) N^3 per pair (what the kernel "
                                     "executes) instead of the survey's N^3; traffic = DRAM bytes per step of all kernels "
-                                    "(ncu, profiles/traffic_%s_r02.json) or null" % args.workload},
+                                    "(ncu, profiles/traffic_%s_r02.json) or null" % wname},
                "clocks": clocks}
-        if world == 1 and not args.no_cpu:
+        if world == 1 and with_cpu:
             arm = CpuArm(w)
             t0 = time.perf_counter()
             arm.sample()
@@ -445,8 +444,43 @@ def run_ours(args, w):
                 arm.sample()
             out["cpu_baseline"] = {"value": float(np.mean(arm.evals_s)), "unit": "elbo_evals/s", "cores": arm.cores,
                                    "kind": "port", "sample": f"{len(arm.evals_s)} samples; " + arm.describe()}
-        print(json.dumps(out), flush=True)
+    else:
+        out = None
     g.close()
+    del d_hyper, d_elbo, d_iters, d_status, d_taken, flush
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; gpyrn_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = measure(args, w, args.workload, args.steps, args.warmup, args.e2e_steps, not args.no_cpu)
+    if args.workload == "c4" and args.scaling == "weak" and not args.no_extra:
+        # The other named single-GPU-sized configurations, measured briefly in the same run (same code path, same
+        # dealing, same JSON fields) so that the driver's 1/2/4/8 series also carries them: C3 (8192 sets per GPU
+        # through the fused small-N kernel) and C2 (one evaluation per GPU: latency).  Outside the headline's timed
+        # region; they do not enter `value`.
+        extra = {}
+        for name, st, wu in (("c3", 2, 1), ("c2", 10, 3)):
+            r = measure(args, dict(WORKLOADS[name]), name, st, wu, 1, False, tag=name)
+            if r is not None:
+                extra[name] = {k: r[k] for k in ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "config",
+                                                 "gpu_launches", "roofline", "e2e")}
+                extra[name]["mean_iterations"] = r["run"]["mean_iterations"]
+        if out is not None:
+            out["also"] = extra
+    if rank == 0:
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -563,12 +597,16 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("GPRN_BENCH_WORKLOAD", "c4"), choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--pool", type=int, default=64, help="strong scaling: sets in the fixed pool (c5: starts per GPU)")
+    ap.add_argument("--pool-per-gpu", type=int, default=0, help="weak scaling: sets per GPU (default: the workload's)")
     ap.add_argument("--slots", type=int, default=0, help="evaluations in flight per GPU (0: workload default / all that fit)")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="cap on the end-to-end steps (default: --steps)")
+    ap.add_argument("--e2e-steps", type=int, default=5, help="cap on the end-to-end steps (0: as many as --steps)")
     ap.add_argument("--maxfev", type=int, default=40, help="c5: objective evaluations per Nelder-Mead start")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="c4: skip the brief C3 / C2 measurements appended as `also`")
     args = ap.parse_args()
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if args.pool_per_gpu:
+        w["pool_per_gpu"] = args.pool_per_gpu
     if args.impl == "reference":
         run_reference(args, w if args.workload != "c5" else WORKLOADS["c5"])
     elif args.workload == "c5":

@@ -264,3 +264,24 @@ class Matern52(covFunction):
 
     def __init__(self, theta: float, ell: float):
         super().__init__(theta, ell)
+
+
+# ---------------------------------------------------------------------------------------------
+# Kernels of the reference that are outside the hot-path scope (Linear, GammaExp,
+# Polynomial, Piecewise, Paciorek, the *Periodic variants; several of them are broken in the reference itself).
+# They exist as names so that user code fails with a clear message instead of an AttributeError.
+# ---------------------------------------------------------------------------------------------
+def _out_of_scope(name, ref_line):
+    def __init__(self, *args):
+        raise NotImplementedError(
+            f"covfunc.{name} (reference gpyrn/covfunc.py:{ref_line}) has no device program in gpyrn_b200: the "
+            "B200 path covers SquaredExponential, Periodic, QuasiPeriodic, RationalQuadratic, Matern32, Matern52, "
+            "WhiteNoise, Constant, RQP, Cosine, Exponential, Derivative(SE/Periodic/QuasiPeriodic), Sum and "
+            "Multiplication.  There is no CPU fallback.")
+    return type(name, (covFunction,), {"__init__": __init__, "__doc__": f"Not available on the B200 path ({name})."})
+
+
+for _name, _line in (("Linear", 399), ("GammaExp", 415), ("Polynomial", 435), ("Piecewise", 458), ("Paciorek", 477),
+                     ("NewPeriodic", 499), ("QuasiNewPeriodic", 522), ("NewRQP", 549), ("HarmonicPeriodic", 579),
+                     ("QuasiHarmonicPeriodic", 610), ("CosPeriodic", 645), ("QuasiCosPeriodic", 668)):
+    globals()[_name] = _out_of_scope(_name, _line)

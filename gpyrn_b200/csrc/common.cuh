@@ -231,16 +231,30 @@ __device__ __forceinline__ void subst_lower_mma(const double* __restrict__ Ls, i
 // potrf64 (default, "v2"): right-looking in 8 block steps of 8 columns -- 16 CTA barriers instead of 64.
 //   Phase A (warps 0-1, thread t = row t): every thread loads the 8x8 diagonal block (broadcast reads) and factors
 //     it redundantly in registers on UNSCALED columns (T[i][k] = L[i][k] L[k][k], pivot p_k = L[k][k]^2: one
-//     reciprocal per pivot on the dependency chain, square roots off it), then solves its own row of the block
-//     column against it by forward substitution and writes the finished L row.
-//   Phase B (all 8 warps): the trailing 8x8 blocks (I >= K > j) get C_IK -= L_Ij L_Kj^T on DMMA m8n8k4.
+//     reciprocal per pivot on the dependency chain, no square root), then solves its own row of the block column
+//     against it by forward substitution and writes the (unscaled) row.
+//   Phase B (all 8 warps): the trailing 8x8 blocks (I >= K > j) get C_IK -= T_Ij diag(1/p) T_Kj^T on DMMA m8n8k4.
+//   The columns are scaled by 1/sqrt(p) once at the end.
 // A genuine substitution / factorisation: no inverse of a block is formed (DESIGN.md "Numerics").
 // Measured against v1 (one barrier per pivot, 64 x 290 ns = 19 us per tile): see profiles/README.md.
 #ifndef GPRN_POTRF_V1
+// 1/x for a positive normal x: hardware seed (MUFU.RCP64H, relative error <= 2^-23) + two Newton steps
+// (2^-23 -> 2^-46 -> below 1 ulp).  Shorter dependency chain than the IEEE division / __drcp_rn sequence, which is
+// what a pivot step waits on.  Non-positive, NaN or subnormal inputs give garbage; the caller's pivot test flags them.
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
 __device__ __forceinline__ void potrf64(const double* Td, int ldd, double* Ls, double* __restrict__ rd,
                                         double* __restrict__ col, double* __restrict__ pivs, int* bad) {
-    (void)col;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double* sinv = col;                    // 1 / pivot of the finished columns (64 doubles of the scratch)
     if (Td != Ls || ldd != LDT) {          // bring the tile into Ls with stride LDT (alias-safe)
         const int r = tid >> 2, q4 = tid & 3;
         double a[16];
@@ -251,6 +265,8 @@ __device__ __forceinline__ void potrf64(const double* Td, int ldd, double* Ls, d
         for (int u = 0; u < 16; u++) Ls[r * LDT + q4 + 4 * u] = a[u];
         __syncthreads();
     }
+    // The tile is factored on UNSCALED columns, T[i][k] = L[i][k] * L[k][k] with pivots p_k = L[k][k]^2 (as in v1):
+    // a pivot step then needs one reciprocal and no square root; the columns are scaled once at the end.
 #define GPRN_PT(u, w) T[(u) * ((u) + 1) / 2 + (w)]
     for (int j = 0; j < 8; j++) {
         const int c0 = 8 * j;
@@ -268,9 +284,10 @@ __device__ __forceinline__ void potrf64(const double* Td, int ldd, double* Ls, d
             }
             // every read of the diagonal block precedes every write of this phase (rows c0..c0+7 are rewritten)
             asm volatile("bar.sync 1, 64;" ::: "memory");
+            // 8x8 diagonal block, redundantly in every thread (registers only; the warp pays for one thread)
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                inv[k] = __drcp_rn(GPRN_PT(k, k));
+                inv[k] = rcp_fast(GPRN_PT(k, k));
 #pragma unroll
                 for (int i = k + 1; i < 8; i++) {
                     const double t = GPRN_PT(i, k) * inv[k];
@@ -278,7 +295,8 @@ __device__ __forceinline__ void potrf64(const double* Td, int ldd, double* Ls, d
                     for (int c = k + 1; c <= i; c++) GPRN_PT(i, c) = fma(-t, GPRN_PT(c, k), GPRN_PT(i, c));
                 }
             }
-            // row solve  xs_k = a_k - sum_{c<k} (xs_c / p_c) T[k][c]   (xs_k = L[t][c0+k] L[c0+k][c0+k])
+            // own row of the block column:  xs_k = a_k - sum_{c<k} (xs_c / p_c) T[k][c]   (unscaled, like T).
+            // For a row of the diagonal block itself this reproduces T[u][k] (k <= u) with the same operations.
 #pragma unroll
             for (int k = 0; k < 8; k++) {
 #pragma unroll
@@ -289,25 +307,22 @@ __device__ __forceinline__ void potrf64(const double* Td, int ldd, double* Ls, d
                 const int u = tid - c0;    // 0..7: row of the diagonal block; >= 8: row below it
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    const double p = GPRN_PT(k, k);
-                    const double sq = sqrt(p);
-                    const double rs = __drcp_rn(sq);
-                    double val = a[k] * rs;
                     if (k == u) {
-                        val = sq;
+                        const double p = GPRN_PT(k, k);
                         pivs[tid] = p;
-                        rd[tid] = rs;
+                        sinv[tid] = inv[k];
                         if (!(p > 0.0)) *bad = 1;
                     }
-                    if (k > u) val = 0.0;
-                    Ls[tid * LDT + c0 + k] = val;
+                    Ls[tid * LDT + c0 + k] = a[k];
                 }
             }
         }
         __syncthreads();
         if (j < 7) {
+            // trailing blocks (I >= K > j):  C_IK -= T_Ij diag(1/p) T_Kj^T  on DMMA m8n8k4
             const int nb = 7 - j, cnt = nb * (nb + 1) / 2;
             const int r = lane >> 2, c = lane & 3;
+            const double s0 = -sinv[c0 + c], s1 = -sinv[c0 + c + 4];
             for (int pi = warp; pi < cnt; pi += 8) {
                 int ii = 0, kk = pi;
                 while (kk > ii) { kk -= ii + 1; ii++; }
@@ -317,18 +332,27 @@ __device__ __forceinline__ void potrf64(const double* Td, int ldd, double* Ls, d
                 double acc[2] = {cv.x, cv.y};
                 const double* ap = Ls + (8 * I + r) * LDT + c0 + c;
                 const double* bp = Ls + (8 * K + r) * LDT + c0 + c;
-                dmma884(acc, -ap[0], bp[0]);
-                dmma884(acc, -ap[4], bp[4]);
+                dmma884(acc, ap[0] * s0, bp[0]);
+                dmma884(acc, ap[4] * s1, bp[4]);
                 *reinterpret_cast<double2*>(cp) = make_double2(acc[0], acc[1]);
             }
             __syncthreads();
         }
     }
 #undef GPRN_PT
-    // blocks above the diagonal were never touched: they still hold the input's upper triangle
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int r = e >> 6, c = e & 63;
-        if ((c >> 3) > (r >> 3)) Ls[r * LDT + c] = 0.0;
+    // scale the columns: L[r][c] = T[r][c] / sqrt(p_c), L[c][c] = sqrt(p_c), zeros above the diagonal
+    if (tid < NB) rd[tid] = rcp_fast(sqrt(pivs[tid]));
+    __syncthreads();
+    {
+        const int r = tid >> 2, q4 = tid & 3;
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            const int cc = q4 + 4 * u;
+            double v = 0.0;
+            if (cc < r) v = Ls[r * LDT + cc] * rd[cc];
+            else if (cc == r) v = sqrt(pivs[r]);
+            Ls[r * LDT + cc] = v;
+        }
     }
     __syncthreads();
 }

@@ -21,32 +21,61 @@ _pool_serial = itertools.count()
 
 
 class SharedCounter:
-    """Atomic work counter shared by all ranks of the process group: ``next()`` returns 0, 1, 2, ... exactly once
-    across the whole group and -1 once ``total`` has been handed out.  Backed by ``store.add`` of the rendezvous
-    store (TCPStore), which is an atomic fetch-add served by rank 0; a plain local counter without a process group."""
+    """Atomic work counter shared by all ranks of the process group: ``next()`` returns every index of
+    ``range(total)`` exactly once across the whole group and -1 once the pool is exhausted.  Backed by ``store.add`` of
+    the rendezvous store (TCPStore), an atomic fetch-add served by rank 0; a plain local counter without a process
+    group.
 
-    def __init__(self, total, key, store=None):
+    Indices are reserved in grains, one store round trip each: the FIRST reservation takes ``first`` consecutive
+    indices (a rank's initial fill: its workspace slots, at most its fair share ceil(total / world) -- a GPU whose
+    memory could hold the whole pool must not drain it), every later one ``grain`` (small, so that the tail of the
+    pool goes to whichever GPU frees a slot first).  A pool of thousands of cheap sets uses a coarser grain than one
+    of a few expensive sets: a round trip costs tens of microseconds."""
+
+    def __init__(self, total, key, store=None, first=1, grain=1):
         import torch.distributed as dist
         self.total = int(total)
         self.key = f"gprn_pool/{key}"
         self.store = store
         self.local = 0
+        self.first, self.grain = max(1, int(first)), max(1, int(grain))
+        self.reserve = []              # indices reserved and not handed out yet
+        self.trips = 0
         self.handed = []
         if store is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             self.store = dist.distributed_c10d._get_default_store()
 
-    def next(self):
+    def _reserve(self, n):
         if self.store is None:
-            i = self.local
-            self.local += 1
+            lo = self.local
+            self.local += n
         else:
-            i = self.store.add(self.key, 1) - 1
-        if i >= self.total:
-            return -1
+            lo = self.store.add(self.key, n) - n
+        self.trips += 1
+        return range(lo, min(lo + n, self.total))
+
+    def next(self):
+        if not self.reserve:
+            if self.trips and self.local >= self.total and self.store is None:
+                return -1
+            self.reserve = list(self._reserve(self.first if self.trips == 0 else self.grain))[::-1]
+            if not self.reserve:
+                return -1
+        i = self.reserve.pop()
         self.handed.append(i)
         return i
 
     __call__ = next
+
+
+def dealing_grains(B, world, slots):
+    """(first, grain) of SharedCounter for a pool of B sets over `world` ranks with `slots` evaluations in flight per
+    rank (0: unknown / as many as fit): the initial fill is a contiguous block of min(slots, fair share) sets, the
+    rest is dealt in grains of 1 (few large sets) up to 64 (thousands of small ones)."""
+    share = -(-B // max(1, world))
+    first = share if slots <= 0 else min(slots, share)
+    grain = max(1, min(64, first // 16))
+    return first, grain
 
 
 def shard_indices(B, world_size, rank, mode="strided"):
@@ -191,8 +220,11 @@ def elbo_pool_sharded(gprn, parameters, max_iter=None, slots=0, key=None, group=
 
     P = np.atleast_2d(np.asarray(parameters, dtype=float))
     B = P.shape[0]
-    rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
-    counter = SharedCounter(B, next(_pool_serial) if key is None else key)
+    on = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if on else 0
+    world = dist.get_world_size(group) if on else 1
+    first, grain = dealing_grains(B, world, slots)
+    counter = SharedCounter(B, next(_pool_serial) if key is None else key, first=first, grain=grain)
     if evaluate is None:
         elbo, iters, status, taken = gprn.ELBO_batch(P, max_iter=max_iter, return_info=True, slots=slots,
                                                      work_source=counter)

@@ -62,6 +62,10 @@ def test_shared_counter_single_process():
     c = D.SharedCounter(3, "solo")
     assert [c.next(), c.next(), c(), c.next(), c.next()] == [0, 1, 2, -1, -1]
     assert c.handed == [0, 1, 2]
+    c = D.SharedCounter(11, "grains", first=4, grain=3)       # reservations: [0..4) [4..7) [7..10) [10..11)
+    assert [c.next() for _ in range(13)] == list(range(11)) + [-1, -1] and c.trips >= 4
+    assert D.dealing_grains(16, 2, 0) == (8, 1) and D.dealing_grains(64, 8, 4) == (4, 1)
+    assert D.dealing_grains(16384, 2, 13107) == (8192, 64)
     P = np.arange(12.0).reshape(4, 3)
 
     def evaluate(PP, counter):
@@ -113,7 +117,7 @@ def _worker(rank, world, port, B, q):
             e[i], it[i], taken[i] = PP[i].sum(), 4 + i % 3, True
         return e, it, st, taken
 
-    e, it, st, owner = D.elbo_pool_sharded(None, P, key="t1", evaluate=evaluate)
+    e, it, st, owner = D.elbo_pool_sharded(None, P, key="t1", evaluate=evaluate, slots=4)     # 4 in flight: dynamic tail
     ok = ok and np.allclose(e, P.sum(axis=1)) and np.array_equal(it, 4 + np.arange(B) % 3) and np.all(st == 0)
     ok = ok and set(np.unique(owner).tolist()) <= {0, 1} and np.all(owner >= 0)
     if B >= 32:

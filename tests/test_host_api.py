@@ -253,3 +253,21 @@ def test_trace_analysis_tool_on_synthetic_records(tmp_path, capsys):
     assert "syrk_outer" in out and "trsm_col" in out
     gemm = float(re.search(r"GEMM-class CTA .* resident: ([0-9.]+) %", out).group(1))
     assert 70.0 < gemm < 80.0            # SM 0 always, SM 1 half of the time
+
+
+def test_out_of_scope_kernels_fail_loudly():
+    """the reference's other kernels exist as names and raise a clear NotImplementedError."""
+    for name in ("Linear", "GammaExp", "Polynomial", "Piecewise", "Paciorek", "NewPeriodic", "QuasiNewPeriodic",
+                 "NewRQP", "HarmonicPeriodic", "QuasiHarmonicPeriodic", "CosPeriodic", "QuasiCosPeriodic"):
+        with pytest.raises(NotImplementedError, match="no device program"):
+            getattr(covfunc, name)(1.0, 2.0)
+
+
+def test_reference_side_stub_is_syntactically_complete():
+    """integration/gpyrn_b200_stub.py (the binding INTEGRATION.md shows) binds only symbols the header declares."""
+    src = open(os.path.join(ROOT, "integration", "gpyrn_b200_stub.py")).read()
+    used = set(re.findall(r"_L\.(gprn_[a-z_]+)", src))
+    hdr = open(os.path.join(ROOT, "include", "gprn_b200.h")).read()
+    for name in used:
+        assert re.search(r"\b" + name + r"\s*\(", hdr), name
+    assert {"gprn_create", "gprn_set_model", "gprn_elbo_batched", "gprn_predict"} <= used

@@ -45,6 +45,7 @@ def test_stub_on_unmodified_reference(shape, capsys):
     # the reference's own CPU path
     e_ref, mu_ref, var_ref, it_ref = g.ELBOcalc()
     pm_ref, pv_ref = g._Prediction(tstar=tstar, mu=np.asarray(mu_ref), var=np.asarray(var_ref))
+    val_ref = g.nELBO(g.get_parameters())              # the reference's warm start from its converged state
     g._mu = g._var = None
     # the same object, hot path on the B200
     stub.patch(g)
@@ -56,10 +57,12 @@ def test_stub_on_unmodified_reference(shape, capsys):
         pm, pv = g._Prediction(tstar=tstar, mu=np.asarray(mu_ref), var=np.asarray(var_ref))
         assert np.max(np.abs(pm - pm_ref)) <= 1e-8 * np.max(np.abs(pm_ref))
         assert np.max(np.abs(pv - pv_ref)) <= 1e-8 * np.max(np.abs(pv_ref))
-        # reference drivers on top of the patched methods: warm-started nELBO, ELBO property
+        # reference drivers on top of the patched methods: nELBO warm-started from the same converged state,
+        # the ELBO property
+        g._mu, g._var = np.asarray(mu_ref), np.asarray(var_ref)
         val = g.nELBO(g.get_parameters())
-        assert np.isfinite(val) and abs(-val - e_ref) <= 2e-3 * abs(e_ref)      # stop rule is 1e-3 on the ELBO trace
-        assert g.ELBO == pytest.approx(-val, rel=2e-3)
+        assert abs(val - val_ref) <= 1e-10 * abs(val_ref), (val, val_ref)
+        assert abs(g.ELBO - e_ref) <= 1e-10 * abs(e_ref)
     finally:
         stub.unpatch(g)
     capsys.readouterr()

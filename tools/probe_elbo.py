@@ -17,7 +17,8 @@ K = {"QP": covfunc.QuasiPeriodic, "M52": covfunc.Matern52, "SE": covfunc.Squared
 g.set_components([K[s[0]](*s[1:]) for s in m.nodes], [K[s[0]](*s[1:]) for s in m.weights],
                  [meanfunc.Constant(0.0)] * p, [0.1] * p)
 P = np.concatenate([theta[:, :-p], np.zeros((B, p)), theta[:, -p:]], axis=1)
-g.ELBO_batch(P, max_iter=max_iter)          # warm-up (allocations)
+if not os.environ.get("GPRN_PROBE_NOWARM"):
+    g.ELBO_batch(P, max_iter=max_iter)          # warm-up (allocations)
 _lib.lib().gprn_reset_launch_count(g._h())
 t0 = time.time()
 elbo, iters, status = g.ELBO_batch(P, max_iter=max_iter, return_info=True)
