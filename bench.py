@@ -64,6 +64,8 @@ WORKLOADS = {
                name="C3 synth(N=256,p=4,q=1,QuasiPeriodic node, SE weights), 8192 hyper sets per GPU"),
     "c2": dict(N=500, p=4, q=1, node="QP", pool_per_gpu=1, seed=101, slots=0, anchor=None,
                name="C2 synth(N=500,p=4,q=1,QuasiPeriodic node, SE weights), single ELBOcalc"),
+    "c2b": dict(N=500, p=4, q=1, node="QP", pool_per_gpu=512, seed=101, slots=0, anchor=None,
+                name="C2-size batch: synth(N=500,p=4,q=1,QuasiPeriodic node, SE weights), 512 hyper sets per GPU"),
     "c5": dict(N=2048, p=4, q=2, node="M52", pool_per_gpu=8, seed=103, slots=0, anchor=None,
                name="C5 synth(N=2048,p=4,q=2,Matern52 nodes): lock-step Nelder-Mead sweep + prediction at T=20000"),
 }
@@ -305,6 +307,7 @@ def measure(args, w, wname, steps, warmup, e2e_cap, with_cpu, tag=""):
     B, H = theta.shape
     slots = args.slots if args.slots else w["slots"]
     first, grain = D.dealing_grains(B, world, slots)
+    cap = slots if (slots or world == 1) else first          # never more than the fair share in flight per rank
     g = make_inference(a, w, local)
     P = np.concatenate([theta[:, :-p], np.zeros((B, p)), theta[:, -p:]], axis=1)      # get_parameters order
     L = _lib.lib()
@@ -320,13 +323,16 @@ def measure(args, w, wname, steps, warmup, e2e_cap, with_cpu, tag=""):
     stream = torch.cuda.current_stream()
     serial = [0]
 
-    def step_dev():
-        """One step with the pool resident in HBM: dynamic dealing + the result all-reduce, all on `stream`."""
+    def step_dev(nsets=None):
+        """One step with the pool resident in HBM: dynamic dealing + the result all-reduce, all on `stream`.
+        nsets: evaluate only the first nsets sets of the pool (reduced warm-up of the strong-scaling runs)."""
         serial[0] += 1
-        counter = D.SharedCounter(B, f"{tag}dev{serial[0]}", first=first, grain=grain)
+        nb = B if nsets is None else min(B, nsets)
+        f0, g0 = (first, grain) if nsets is None else D.dealing_grains(nb, world, slots)
+        counter = D.SharedCounter(nb, f"{tag}dev{serial[0]}", first=f0, grain=g0)
         cb = _lib.NEXT_SET_FN(lambda _u: counter.next())
-        _lib.check(L.gprn_elbo_pool(h, B, d_hyper.data_ptr(), 1, None, 1, ctypes.cast(cb, ctypes.c_void_p), None, slots,
-                                    0, -1, d_elbo.data_ptr(), d_iters.data_ptr(), d_status.data_ptr(),
+        _lib.check(L.gprn_elbo_pool(h, nb, d_hyper.data_ptr(), 1, None, 1, ctypes.cast(cb, ctypes.c_void_p), None,
+                                    cap if nsets is None else min(cap, nb) if cap else 0, 0, -1, d_elbo.data_ptr(), d_iters.data_ptr(), d_status.data_ptr(),
                                     d_taken.data_ptr(), 1, stream.cuda_stream))
         mine = d_taken.clone()
         D.reduce_disjoint([d_elbo, d_iters, d_status, d_taken])       # the one collective of the path
@@ -338,7 +344,7 @@ def measure(args, w, wname, steps, warmup, e2e_cap, with_cpu, tag=""):
         torch.cuda.synchronize()
 
     for _ in range(warmup):
-        step_dev()
+        step_dev(args.warmup_pool * world if args.warmup_pool else None)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -367,18 +373,20 @@ def measure(args, w, wname, steps, warmup, e2e_cap, with_cpu, tag=""):
     mine = mine.cpu().numpy().astype(bool)
     assert np.all(taken_all == 1), "every set of the pool must be evaluated by exactly one rank"
     # end to end through the product API (host buffers in, host results out, dynamic dealing, gather included)
-    D.elbo_pool_sharded(g, P[:max(1, min(B, 2))], slots=slots, key=f"{tag}e2e-warm")
-    barrier()
-    e2e_steps = steps if not e2e_cap else min(steps, e2e_cap)
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        e_api, it_api, st_api, owner = D.elbo_pool_sharded(g, P, slots=slots, key=f"{tag}e2e{k}")
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    barrier()
+    e2e_steps = 0 if args.no_e2e else (steps if not e2e_cap else min(steps, e2e_cap))
+    e2e_s = float("nan")
+    if e2e_steps:
+        D.elbo_pool_sharded(g, P[:max(1, min(B, 2))], slots=slots, key=f"{tag}e2e-warm")
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            e_api, it_api, st_api, owner = D.elbo_pool_sharded(g, P, slots=slots, key=f"{tag}e2e{k}")
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        barrier()
+        assert np.array_equal(e_api, elbo_all), "product API and device-pointer entry disagree"
+        assert np.array_equal(it_api, iters_all)
     clocks = sampler.stop() if sampler else None
-    assert np.array_equal(e_api, elbo_all), "product API and device-pointer entry disagree"
-    assert np.array_equal(it_api, iters_all)
     if args.scaling == "weak" and world > 1:
         rep = elbo_all.reshape(world, base)
         assert np.all(rep == rep[0]), "replicas of a set evaluated on different GPUs must agree bit for bit"
@@ -417,6 +425,7 @@ def measure(args, w, wname, steps, warmup, e2e_cap, with_cpu, tag=""):
                        "not_converged_or_failed": int((status_all != 0).sum()),
                        "dealing": f"dynamic: shared counter on the rendezvous store, natural order, first grain {first} then {grain}; "
                                   "result all-reduce inside the timed step",
+                       "warmup_pool": (args.warmup_pool * world) if args.warmup_pool else "whole pool",
                        "sets_per_rank_last_step": [int(x) for x in per_rank[:, 0].tolist()],
                        "iterations_per_rank_last_step": [int(x) for x in per_rank[:, 1].tolist()],
                        "device_ms_per_rank": [float(x) for x in per_rank[:, 2].tolist()],
@@ -424,7 +433,7 @@ def measure(args, w, wname, steps, warmup, e2e_cap, with_cpu, tag=""):
                        "l2": "256 MiB flush between steps; per-step working set (K, L, L^-1 per matrix) >> 126 MB L2"
                              if N >= 1024 or B > 64 else "256 MiB flush between steps",
                        "elbo_checksum": float(np.sum(elbo_all)), "anchor": anchor},
-               "e2e": {"value": B * e2e_steps / (e2e_ms * 1e-3), "unit": "elbo_evals/s", "steps": e2e_steps,
+               "e2e": {"value": B * e2e_steps / (e2e_ms * 1e-3) if e2e_steps else None, "unit": "elbo_evals/s", "steps": e2e_steps,
                        "h2d_bytes_per_step": int(B * H * 8 + p * N * 8), "d2h_bytes_per_step": int(B * 20),
                        "api": "gpyrn_b200.distributed.elbo_pool_sharded -> inference.ELBO_batch (host buffers)"},
                "gpu_launches": int(launches_all), "graph_launches": int(graphs_all),
@@ -602,6 +611,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5, help="cap on the end-to-end steps (0: as many as --steps)")
     ap.add_argument("--maxfev", type=int, default=40, help="c5: objective evaluations per Nelder-Mead start")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end loop (strong-scaling series: value only)")
+    ap.add_argument("--warmup-pool", type=int, default=0,
+                    help="warm-up steps evaluate only the first n sets per GPU of the pool (default: the whole pool)")
     ap.add_argument("--no-extra", action="store_true", help="c4: skip the brief C3 / C2 measurements appended as `also`")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])

@@ -100,6 +100,7 @@ struct gprn_handle {
     int device = 0, N = 0, Np = 0, nt = 0, p = 0, q = 0, M = 0, H = 0, d = 0;
     bool model_set = false;
     bool capturing = false;                     // inside a stream capture (CUDA graph of one iteration)
+    bool small_mode = false;                    // this call runs the fused small-N pipeline (decide_small_path)
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // stream groups: set 0 for the fixed-point iteration, set 1 for the set-up of newly admitted sets, which runs
@@ -109,6 +110,8 @@ struct gprn_handle {
     cudaEvent_t ev_fork[2] = {}, ev_join[2][NAUX] = {};
     cudaStream_t side = nullptr;
     cudaEvent_t ev_side_fork = nullptr, ev_side_join = nullptr;
+    cudaStream_t cross = nullptr;               // cross-node trace terms, beside the start of the weight phase
+    cudaEvent_t ev_cross_fork = nullptr, ev_cross_join = nullptr;
     int64_t launches = 0;
     int64_t graph_launches = 0;
     double last_ms = 0.0;
@@ -140,8 +143,16 @@ struct gprn_handle {
     std::vector<unsigned char> graph_sig;       // bytes of the Engine (workspace addresses + context) they were captured for
 };
 
-static bool use_small_path(const gprn_handle* h) {
-    return h->q == 1 && h->nt <= SMALL_MAX_NT && getenv("GPRN_NO_SMALL") == nullptr;
+// Fused single-kernel pipeline (small.cuh): q == 1 (no cross-node terms, which need the factors in HBM) and
+// N <= 256 always; N <= 512 when the call keeps at least two matrices per SM in flight -- one persistent CTA walks a
+// whole matrix, so a handful of mid-size matrices is better served by the multi-CTA kernels of factor.cuh.
+// Decided per call (decide_small_path) because the workspace layout differs.  GPRN_NO_SMALL=1 disables the path,
+// GPRN_SMALL_MAX_NT=4 restricts it to N <= 256.
+static bool use_small_path(const gprn_handle* h) { return h->small_mode; }
+static bool decide_small_path(const gprn_handle* h, int64_t sets_in_flight) {
+    static const int max_nt = getenv("GPRN_SMALL_MAX_NT") ? atoi(getenv("GPRN_SMALL_MAX_NT")) : SMALL_MAX_NT;
+    if (h->q != 1 || h->nt > std::min(max_nt, SMALL_MAX_NT) || getenv("GPRN_NO_SMALL") != nullptr) return false;
+    return h->nt <= 4 || sets_in_flight * h->M >= 2 * (int64_t)h->num_sms;
 }
 
 static void drop_graphs(gprn_handle* h) {
@@ -247,6 +258,9 @@ extern "C" int gprn_create(int device, int N, int p, int q, const double* time, 
     h->d = N * q * (p + 1);
     CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->cross, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_cross_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_cross_join, cudaEventDisableTiming));
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
     CU(cudaEventCreateWithFlags(&h->ev_side_fork, cudaEventDisableTiming));
@@ -307,6 +321,8 @@ extern "C" int gprn_destroy(gprn_handle* h) {
         for (int g = 0; g < gprn_handle::NAUX; g++) { cudaStreamDestroy(h->aux[a][g]); cudaEventDestroy(h->ev_join[a][g]); }
     }
     cudaStreamDestroy(h->side);
+    cudaStreamDestroy(h->cross);
+    cudaEventDestroy(h->ev_cross_fork); cudaEventDestroy(h->ev_cross_join);
     cudaStreamDestroy(h->own_stream);
     delete h;
     return 0;
@@ -722,10 +738,16 @@ static int launch_iteration(gprn_handle* h, Engine& E, int na, cudaStream_t st, 
     post_kernel<<<dim3(q, na), 256, 0, st>>>(c, E.d_sets, 0, q == 1);
     LAUNCH_CHECK(h);
     if (q > 1) {
-        cross_linear_kernel<<<na, 256, 0, st>>>(c, E.d_sets);
+        // Cross-node trace terms (quirk Q3): GEMM-class work that only the ELBO needs.  It runs on its own stream
+        // beside the latency-bound start of the weight phase (it reads the node matrices' D and X, which the weight
+        // phase does not touch) and is joined before elbo_finish_kernel.
+        CU(cudaEventRecord(h->ev_cross_fork, st));
+        CU(cudaStreamWaitEvent(h->cross, h->ev_cross_fork, 0));
+        cross_linear_kernel<<<na, 256, 0, h->cross>>>(c, E.d_sets);
         LAUNCH_CHECK(h);
-        cross_frob_kernel<<<dim3(nt * nt, q * (q - 1) / 2, na), 128, 2 * TILE_SMEM, st>>>(c, E.XK, E.X, E.d_sets);
+        cross_frob_kernel<<<dim3(nt * nt, q * (q - 1) / 2, na), 128, 2 * TILE_SMEM, h->cross>>>(c, E.XK, E.X, E.d_sets);
         LAUNCH_CHECK(h);
+        CU(cudaEventRecord(h->ev_cross_join, h->cross));
     }
     // weight phase
     prep_weights_kernel<<<dim3(q * p, na), 256, 0, st>>>(c, E.d_sets);
@@ -748,6 +770,7 @@ static int launch_iteration(gprn_handle* h, Engine& E, int na, cudaStream_t st, 
         quad_kernel<<<dim3(M, na), 256, 0, st>>>(c, E.d_sets, 0);
         LAUNCH_CHECK(h);
     }
+    if (q > 1) CU(cudaStreamWaitEvent(st, h->ev_cross_join, 0));
     elbo_finish_kernel<<<na, 256, 0, st>>>(c, E.d_sets);
     LAUNCH_CHECK(h);
     return 0;
@@ -934,6 +957,10 @@ static int elbo_impl(gprn_handle* h, int64_t B, const double* hyper, bool hyper_
     CU(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->own_stream;
     if (max_iter < 0) max_iter = 10000;                       // meanfield.py:615-616
+    {
+        const int cap0 = max_slots > 0 ? max_slots : h->max_slots;
+        h->small_mode = decide_small_path(h, cap0 > 0 ? std::min<int64_t>(B, cap0) : B);
+    }
     int nslot = chunk_size(h, B);
     if (nslot < 1) return fail("gprn_elbo_batched: not enough device memory for one evaluation of this size");
     const int cap = max_slots > 0 ? max_slots : h->max_slots;

@@ -1,21 +1,23 @@
-// small.cuh -- fused per-matrix pipeline for small matrices (Np <= 256, i.e. at most 4x4 tiles of 64).
+// small.cuh -- fused per-matrix pipeline for small and mid-size matrices (Np <= 512, i.e. at most 8x8 tiles of 64).
 //
 // One persistent CTA takes a matrix through the WHOLE per-iteration chain
 //     A = K + diag(D)  ->  L = chol(A)  ->  X = L^-1  ->  g = colnorm2(X),  u = X^T (X v),  logdet(A)
 // and only the vectors g, u and the scalar log-det leave the chip.  K is read from HBM exactly once
-// (lower tiles); L / X live in a 10-tile (320 KB) per-CTA scratch that stays L2 resident
-// (296 CTAs x 320 KB = 95 MB < 126 MB L2) -- X tiles overwrite the L tiles they no longer need.
+// (lower tiles); L / X live in a per-CTA scratch of nt(nt+1)/2 tiles -- 10 tiles (320 KB) for Np = 256, which stays
+// L2 resident (296 CTAs x 320 KB = 95 MB < 126 MB L2); 36 tiles (1.15 MB) for Np = 512, which streams through HBM --
+// and X tiles overwrite the L tiles they no longer need.
 // The building blocks are the same as in factor.cuh: DMMA m8n8k4 tile products (mma_tile), the
 // register-resident 64x64 Cholesky (potrf64) and thread-per-vector substitution (subst_lower).
-// Replaces, for q == 1 and N <= 256, form_a + panel_col + trtri_* + trmv_* (one launch instead of ~10 and
+// Replaces, for q == 1 and N <= 256 (and for N <= 512 when enough matrices are in flight to give every SM its own:
+// gprn_api.cu: decide_small_path), form_a + panel_col + trtri_* + trmv_* (one launch per phase instead of ~10-70 and
 // none of their HBM round trips).  256 threads: warps 0-3 and 4-7 work on two tiles at a time.
 #pragma once
 #include "common.cuh"
 
 namespace gprn {
 
-#define SMALL_MAX_NT 4
-#define SMALL_TILES 10
+#define SMALL_MAX_NT 8
+#define SMALL_TILES (SMALL_MAX_NT * (SMALL_MAX_NT + 1) / 2)
 #define SMALL_LDV 129              // odd strides: the fused kernel keeps the thread-per-vector substitution
 #ifdef GPRN_POTRF_V1
 #define SMALL_LDP 65               // (measured: the DMMA variant is 11 % slower here, 2 CTAs/SM already hide its latency)
@@ -23,8 +25,8 @@ namespace gprn {
 #define SMALL_LDP LDT              // potrf64 v2 works in place on the LDT layout
 #endif
 #define SMALL_SCRATCH_DOUBLES (SMALL_TILES * NB * NB)
-// 3 operand tiles + col(128) + pivs(64) + rd(64) + gacc(256) + zacc(256) + vloc(256)
-#define SMALL_SMEM ((3 * NB * LDT + 4 * NB + 3 * SMALL_MAX_NT * NB) * sizeof(double))
+// 3 operand tiles + col(128) + pivs(64) + rd(64) + gacc(Np) + zacc(Np): 112 KB, two CTAs per SM
+#define SMALL_SMEM ((3 * NB * LDT + 4 * NB + 2 * SMALL_MAX_NT * NB) * sizeof(double))
 
 #ifdef GPRN_TRACE
 __device__ unsigned long long g_small_phase[16];
@@ -71,7 +73,6 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
     double* rd = pivs + NB;
     double* gacc = rd + NB;            // [Np]
     double* zacc = gacc + SMALL_MAX_NT * NB;
-    double* vloc = zacc + SMALL_MAX_NT * NB;
     __shared__ int bad;
     const int Np = a.Np, nt = Np / NB;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -93,10 +94,10 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
         __syncthreads();
 
         // ================= Cholesky, left-looking over tile columns =================
-        // Column k is done in two sub-rounds of two tiles: s = 0 -> (k, k+1), s = 1 -> (k+2, k+3); warps 0-3 take
+        // Column k is done in sub-rounds of two tiles: s = 0 -> (k, k+1), s = 1 -> (k+2, k+3), ...; warps 0-3 take
         // the first tile of a sub-round, warps 4-7 the second.  One accumulator set is live at a time.
         for (int k = 0; k < nt; k++) {
-            for (int s = 0; s < 2 && k + 2 * s < nt; s++) {
+            for (int s = 0; k + 2 * s < nt; s++) {
                 const int it = k + 2 * s + grp;
                 const bool have = it < nt;
                 SMALL_PH(1);
@@ -195,10 +196,10 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
         if (!a.do_inverse) continue;
 
         // ================= inverse by block rows; X tiles overwrite the L tiles =================
+        const double* vglob = a.vv + (size_t)id * Np;      // right-hand side v: broadcast reads, L1 / L2 resident
         for (int e = tid; e < Np; e += 256) {
             gacc[e] = 0.0;
             zacc[e] = 0.0;
-            vloc[e] = a.vv[(size_t)id * Np + e];
         }
         __syncthreads();
         for (int i = 0; i < nt; i++) {
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
                     for (int g2 = 0; g2 < 2; g2++) {
                         const int jj = j0 + g2;
                         if (jj <= i)
-                            for (int n = 0; n < NB; n++) sz = fma(V[m * SMALL_LDV + g2 * NB + n], vloc[jj * NB + n], sz);
+                            for (int n = 0; n < NB; n++) sz = fma(V[m * SMALL_LDV + g2 * NB + n], vglob[jj * NB + n], sz);
                     }
                     zacc[i * NB + m] += sz;
                 }
@@ -268,18 +269,16 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
             }
         }
         SMALL_PH(11);
-        // u_j[n] = sum_{i >= j} sum_m X_ij[m][n] z_i[m]   (X tiles from the L2-resident scratch)
-        {
-            const int j = tid >> 6, n = tid & 63;
-            if (j < nt) {
-                double su = 0.0;
-                for (int i = j; i < nt; i++) {
-                    const double* xt = small_tile(sc, i, j);
-                    for (int m = 0; m < NB; m++) su = fma(xt[m * NB + n], zacc[i * NB + m], su);
-                }
-                a.uv[(size_t)id * Np + tid] = su;
-                a.gv[(size_t)id * Np + tid] = gacc[tid];
+        // u_j[n] = sum_{i >= j} sum_m X_ij[m][n] z_i[m]   (X tiles from the scratch)
+        for (int e = tid; e < Np; e += 256) {
+            const int j = e >> 6, n = e & 63;
+            double su = 0.0;
+            for (int i = j; i < nt; i++) {
+                const double* xt = small_tile(sc, i, j);
+                for (int m = 0; m < NB; m++) su = fma(xt[m * NB + n], zacc[i * NB + m], su);
             }
+            a.uv[(size_t)id * Np + e] = su;
+            a.gv[(size_t)id * Np + e] = gacc[e];
         }
         __syncthreads();
         SMALL_PH(0);

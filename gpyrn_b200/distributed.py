@@ -226,7 +226,10 @@ def elbo_pool_sharded(gprn, parameters, max_iter=None, slots=0, key=None, group=
     first, grain = dealing_grains(B, world, slots)
     counter = SharedCounter(B, next(_pool_serial) if key is None else key, first=first, grain=grain)
     if evaluate is None:
-        elbo, iters, status, taken = gprn.ELBO_batch(P, max_iter=max_iter, return_info=True, slots=slots,
+        # a rank never holds more than its fair share in flight: a GPU whose memory fits the whole pool would
+        # otherwise drain the counter before the other ranks get going
+        cap = slots if (slots or world == 1) else first
+        elbo, iters, status, taken = gprn.ELBO_batch(P, max_iter=max_iter, return_info=True, slots=cap,
                                                      work_source=counter)
     else:
         elbo, iters, status, taken = evaluate(P, counter)

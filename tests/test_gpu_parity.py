@@ -674,3 +674,31 @@ def test_chunked_prediction_with_whitenoise_square_quirk(monkeypatch):
     pm2, pv2 = g._Prediction(tstar=m.time, mu=mu, var=var)
     assert rel(pm2, om) < 1e-8 and rel(pv2, ov) < 1e-8
     g.close()
+
+
+@pytest.mark.parametrize("p,tol_oracle", [(2, 1e-10), (1, 2e-8)])
+def test_mid_n_fused_path_matches_multi_kernel_path_and_oracle(p, tol_oracle):
+    """256 < N <= 512, q = 1 with enough matrices in flight runs the fused single-kernel pipeline (small.cuh, nt up to
+    8); a single evaluation of the same set runs the multi-kernel path.  The two device paths must agree to 1e-10 with
+    identical iteration counts, and with the oracle to 1e-10 (p = 2: 5 iterations, |ELBO| ~ 2e3).
+    The p = 1 case is the ill-conditioned one: 110-130 iterations and an ELBO of 4 ... 50 left over from terms of
+    order 1e3, for which the ORACLE ITSELF moves by 3e-9 between two hosts (set 0: 3.9144956393 in the build container,
+    3.9144956423 on the GPU box, different BLAS kernels); there the bar against the oracle is 2e-8 and the device
+    paths are still held to 1e-10 against each other."""
+    m = orc.synth(330, p, 1, seed=5, node="QP")           # Np = 384: 6 x 6 tiles
+    B = 160                                                # 160 sets x (p + 1) matrices >= 2 x 148 SMs: fused path
+    theta = orc.perturbed_hyper_sets(m, B, 13)
+    g = from_oracle_model(m)
+    P = full_parameters(m, theta)
+    elbo, iters, status = g.ELBO_batch(P, return_info=True)
+    assert np.all(status == 0) and np.all(np.isfinite(elbo))
+    for b in (0, 7, B - 1):
+        g.set_parameters(P[b])
+        e1, _, _, it1 = g.ELBOcalc()                        # B = 1: multi-kernel path
+        assert it1 == iters[b] and abs(e1 - elbo[b]) <= 1e-10 * abs(e1), (b, e1, elbo[b])
+        e_o, _, _, it_o = orc.elbo_calc(orc.model_with_hyper(m, theta[b]))
+        assert it_o == iters[b] and abs(elbo[b] - e_o) <= tol_oracle * abs(e_o), (b, elbo[b], e_o)
+    # continuous batching through the fused path: refilled slots give the same bits
+    got = g.ELBO_batch(P, slots=150)
+    assert np.array_equal(got, elbo)
+    g.close()
