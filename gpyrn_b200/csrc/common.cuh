@@ -116,6 +116,112 @@ __device__ __forceinline__ void mma_tile_scaled(double (&acc)[4][4][2], const do
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-resident tile routines: a 64x64 tile is owned by FOUR warps, warp w4 holding the 16 x 64 slab of rows
+// 16*w4 .. 16*w4+15 in DMMA accumulator layout,
+//     acc[x][y][e] = T[16*w4 + 8x + r][8y + 2c + e],     r = lane / 4, c = lane % 4.
+// Every warp then owns COMPLETE rows, so a triangular solve from the right (X L^T = T: the Cholesky panel solve and,
+// with the inverse factor stored transposed, the row sweep of the inverse) runs inside the warp's registers: no
+// staging of the right-hand sides in shared memory, no transposition, no CTA barrier.  oracle/warp_model.py is a
+// lane-level numpy model of these routines (tests/test_warp_model.py checks the index arithmetic on the CPU).
+// ------------------------------------------------------------------------------------------------
+
+// acc(16 x 64 slab of warp w4) += As[slab rows][k] * Bs[n][k]^T  (As, Bs: 64 x 64 in shared memory, stride LDT).
+template <bool NEG>
+__device__ __forceinline__ void mma_slab(double (&acc)[2][8][2], const double* __restrict__ As,
+                                         const double* __restrict__ Bs, int w4, int lane) {
+    const int r = lane >> 2, c = lane & 3;
+    const double* ap = As + (w4 * 16 + r) * LDT + c;
+    const double* bp = Bs + r * LDT + c;
+#pragma unroll 2
+    for (int k0 = 0; k0 < NB; k0 += 4) {
+        double a[2], b[8];
+#pragma unroll
+        for (int x = 0; x < 2; x++) {
+            a[x] = ap[x * 8 * LDT + k0];
+            if (NEG) a[x] = -a[x];
+        }
+#pragma unroll
+        for (int y = 0; y < 8; y++) b[y] = bp[y * 8 * LDT + k0];
+#pragma unroll
+        for (int x = 0; x < 2; x++)
+#pragma unroll
+            for (int y = 0; y < 8; y++) dmma884(acc[x][y], a[x], b[y]);
+    }
+}
+
+// Solve  X L^T = T  in place for the warp's slab (forward substitution along the columns, right-looking over the
+// eight 8-column blocks).  Ls: L, 64 x 64 lower triangular in shared memory (stride LDT); rd[j] = 1 / L[j][j].
+// Block step y:  (a) the 8 x 8 diagonal block is solved inside each quad (the four lanes of a quad hold one row's
+// eight values of the block): column j is finished by its owner (multiplication by the reciprocal diagonal), broadcast
+// to the quad by one shuffle and eliminated from the columns j' > j by the lanes that own them -- scalar FMAs in
+// ascending column order, exactly the arithmetic of subst_lower_mma; (b) the solved block (negated, turned into A
+// fragments by two more quad shuffles per k-step) updates the blocks y' > y,  T[:, y'] -= X[:, y] L[y', y]^T : two
+// DMMA k-steps per (row block, y'), B fragments straight from Ls -- block y + 1 at once, the others interleaved with
+// the column steps of the next solve.  A genuine substitution: no inverse of a block is
+// formed.  ymin: column blocks below ymin are zero in T for all rows of the warp (identity right-hand sides).
+// (A variant that gathers the eight values into every lane and solves the block redundantly halves the shuffle
+// latency but needs ~170 registers; this one takes 102.)
+__device__ __forceinline__ void trsm_rows_inreg(double (&acc)[2][8][2], const double* __restrict__ Ls,
+                                                const double* __restrict__ rd, int lane, int ymin = 0) {
+    const int r = lane >> 2, c = lane & 3, qbase = lane & ~3;
+    double pa0[2] = {0.0, 0.0}, pa1[2] = {0.0, 0.0};     // A fragments of the previous block (its deferred updates)
+#pragma unroll
+    for (int y = 0; y < 8; y++) {
+        if (y < ymin) continue;                       // warp-uniform
+        const double* Ld = Ls + (8 * y + 2 * c) * LDT + 8 * y;     // this lane's two rows of the diagonal block of L
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const double rdj = rd[8 * y + j];
+            const double l0 = Ld[j], l1 = Ld[LDT + j];
+#pragma unroll
+            for (int x = 0; x < 2; x++) {
+                double xj = ((j & 1) ? acc[x][y][1] : acc[x][y][0]) * rdj;
+                xj = __shfl_sync(0xffffffffu, xj, qbase | (j >> 1));
+                if (c == (j >> 1)) {
+                    if (j & 1) acc[x][y][1] = xj;
+                    else acc[x][y][0] = xj;
+                }
+                if (2 * c > j) acc[x][y][0] = fma(-l0, xj, acc[x][y][0]);
+                if (2 * c + 1 > j) acc[x][y][1] = fma(-l1, xj, acc[x][y][1]);
+            }
+            // software pipelining: the updates that block y-1 owes to the blocks beyond y are issued between the
+            // column steps of block y, whose mul -> shuffle -> fma chain (46 cycles a step) leaves the FP64 pipe idle;
+            // only the update of block y itself was applied before this solve started.  Every target still receives
+            // its updates in ascending source order.
+            if (y >= 1 && y + 1 + j <= 7 && y > ymin) {
+                const int yy = y + 1 + j;
+                const double b0 = Ls[(8 * yy + r) * LDT + 8 * (y - 1) + c], b1 = Ls[(8 * yy + r) * LDT + 8 * (y - 1) + 4 + c];
+#pragma unroll
+                for (int x = 0; x < 2; x++) {
+                    dmma884(acc[x][yy], pa0[x], b0);
+                    dmma884(acc[x][yy], pa1[x], b1);
+                }
+            }
+        }
+        if (y == 7) break;
+        // A fragments of the solved block: lane (r, c) needs columns c and 4 + c of row r, held by lanes c/2 and 2 + c/2
+#pragma unroll
+        for (int x = 0; x < 2; x++) {
+            const double v0 = __shfl_sync(0xffffffffu, acc[x][y][0], qbase | (c >> 1));
+            const double v1 = __shfl_sync(0xffffffffu, acc[x][y][1], qbase | (c >> 1));
+            const double w0 = __shfl_sync(0xffffffffu, acc[x][y][0], qbase | 2 | (c >> 1));
+            const double w1 = __shfl_sync(0xffffffffu, acc[x][y][1], qbase | 2 | (c >> 1));
+            pa0[x] = -((c & 1) ? v1 : v0);
+            pa1[x] = -((c & 1) ? w1 : w0);
+        }
+        {   // the next block needs this one's update now
+            const int yy = y + 1;
+            const double b0 = Ls[(8 * yy + r) * LDT + 8 * y + c], b1 = Ls[(8 * yy + r) * LDT + 8 * y + 4 + c];
+#pragma unroll
+            for (int x = 0; x < 2; x++) {
+                dmma884(acc[x][yy], pa0[x], b0);
+                dmma884(acc[x][yy], pa1[x], b1);
+            }
+        }
+    }
+}
+
 // Forward substitution  L y = g  for ONE vector per thread, everything in shared memory.
 //   Ls : 64x64 lower-triangular tile, element (m,k) at Ls[m*lds + k]   (read by broadcast)
 //   rd : reciprocals of the diagonal of Ls (64 values)
@@ -228,7 +334,8 @@ __device__ __forceinline__ void subst_lower_mma(const double* __restrict__ Ls, i
 //   rd  : output, 1 / L[c][c];   col: scratch 128 doubles (v1 only);   pivs: output, pivots L[c][c]^2
 //   bad : set to 1 when a pivot is not positive (caller zeroes it)
 //
-// potrf64 (default, "v2"): right-looking in 8 block steps of 8 columns -- 16 CTA barriers instead of 64.
+// potrf64 ("v2" arithmetic; the default is its look-ahead form "v3" below): right-looking in 8 block steps of 8
+// columns -- 16 CTA barriers instead of 64.
 //   Phase A (warps 0-1, thread t = row t): every thread loads the 8x8 diagonal block (broadcast reads) and factors
 //     it redundantly in registers on UNSCALED columns (T[i][k] = L[i][k] L[k][k], pivot p_k = L[k][k]^2: one
 //     reciprocal per pivot on the dependency chain, no square root), then solves its own row of the block column
@@ -251,100 +358,132 @@ __device__ __forceinline__ double rcp_fast(double x) {
     return r;
 }
 
-__device__ __forceinline__ void potrf64(const double* Td, int ldd, double* Ls, double* __restrict__ rd,
-                                        double* __restrict__ col, double* __restrict__ pivs, int* bad) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    double* sinv = col;                    // 1 / pivot of the finished columns (64 doubles of the scratch)
-    if (Td != Ls || ldd != LDT) {          // bring the tile into Ls with stride LDT (alias-safe)
-        const int r = tid >> 2, q4 = tid & 3;
-        double a[16];
-#pragma unroll
-        for (int u = 0; u < 16; u++) a[u] = Td[r * ldd + q4 + 4 * u];
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < 16; u++) Ls[r * LDT + q4 + 4 * u] = a[u];
-        __syncthreads();
-    }
-    // The tile is factored on UNSCALED columns, T[i][k] = L[i][k] * L[k][k] with pivots p_k = L[k][k]^2 (as in v1):
-    // a pivot step then needs one reciprocal and no square root; the columns are scaled once at the end.
+// potrf64 (default, "v3"): the arithmetic of v2, operation for operation (bit-identical factors), with the
+// dependency chain shortened:
+//   * look-ahead: after block step j only the NEXT block column (I, j+1) is updated by all warps; warps 0-1 then start
+//     phase A of step j+1 while warps 2-7 apply step j to the remaining blocks (I >= K >= j+2) -- the trailing update
+//     leaves the critical path (every block still receives its updates in ascending j);
+//   * phase A eliminates the thread's own row together with the 8x8 diagonal block (column by column: independent
+//     FMAs) instead of solving it afterwards with one serial chain per element.
+// Measured in isolation (tools/small_micro.cu): see profiles/README.md.
+__device__ __forceinline__ void potrf64_phase_a(double* Ls, double* __restrict__ sinv, double* __restrict__ pivs,
+                                                int* bad, int j, int tid) {
+    const int c0 = 8 * j;
+    double T[36], a[8];
 #define GPRN_PT(u, w) T[(u) * ((u) + 1) / 2 + (w)]
-    for (int j = 0; j < 8; j++) {
-        const int c0 = 8 * j;
-        if (tid < NB) {                    // warps 0-1, converged: thread = row of the tile
-            double T[36], inv[8], a[8], y[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++)
+    for (int u = 0; u < 8; u++)
 #pragma unroll
-                for (int w = 0; w <= u; w++) GPRN_PT(u, w) = Ls[(c0 + u) * LDT + c0 + w];
+        for (int w = 0; w <= u; w++) GPRN_PT(u, w) = Ls[(c0 + u) * LDT + c0 + w];
 #pragma unroll
-            for (int k = 0; k < 8; k += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(Ls + tid * LDT + c0 + k);
-                a[k] = v.x;
-                a[k + 1] = v.y;
-            }
-            // every read of the diagonal block precedes every write of this phase (rows c0..c0+7 are rewritten)
-            asm volatile("bar.sync 1, 64;" ::: "memory");
-            // 8x8 diagonal block, redundantly in every thread (registers only; the warp pays for one thread)
+    for (int k = 0; k < 8; k += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(Ls + tid * LDT + c0 + k);
+        a[k] = v.x;
+        a[k + 1] = v.y;
+    }
+    // every read of the diagonal block precedes every write of this phase (rows c0..c0+7 are rewritten)
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+    // 8x8 diagonal block, redundantly in every thread (registers only; the warp pays for one thread), and the
+    // thread's own row of the block column with it:  xs_k = a_k - sum_{c<k} (xs_c / p_c) T[k][c]   (unscaled, like T).
+    // For a row of the diagonal block itself this reproduces T[u][k] (k <= u) with the same operations.
+    double inv[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                inv[k] = rcp_fast(GPRN_PT(k, k));
+    for (int k = 0; k < 8; k++) {
+        inv[k] = rcp_fast(GPRN_PT(k, k));
 #pragma unroll
-                for (int i = k + 1; i < 8; i++) {
-                    const double t = GPRN_PT(i, k) * inv[k];
+        for (int i = k + 1; i < 8; i++) {
+            const double t = GPRN_PT(i, k) * inv[k];
 #pragma unroll
-                    for (int c = k + 1; c <= i; c++) GPRN_PT(i, c) = fma(-t, GPRN_PT(c, k), GPRN_PT(i, c));
-                }
-            }
-            // own row of the block column:  xs_k = a_k - sum_{c<k} (xs_c / p_c) T[k][c]   (unscaled, like T).
-            // For a row of the diagonal block itself this reproduces T[u][k] (k <= u) with the same operations.
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-#pragma unroll
-                for (int c = 0; c < k; c++) a[k] = fma(-y[c], GPRN_PT(k, c), a[k]);
-                y[k] = a[k] * inv[k];
-            }
-            if (tid >= c0) {
-                const int u = tid - c0;    // 0..7: row of the diagonal block; >= 8: row below it
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    if (k == u) {
-                        const double p = GPRN_PT(k, k);
-                        pivs[tid] = p;
-                        sinv[tid] = inv[k];
-                        if (!(p > 0.0)) *bad = 1;
-                    }
-                    Ls[tid * LDT + c0 + k] = a[k];
-                }
-            }
+            for (int c = k + 1; c <= i; c++) GPRN_PT(i, c) = fma(-t, GPRN_PT(c, k), GPRN_PT(i, c));
         }
-        __syncthreads();
-        if (j < 7) {
-            // trailing blocks (I >= K > j):  C_IK -= T_Ij diag(1/p) T_Kj^T  on DMMA m8n8k4
-            const int nb = 7 - j, cnt = nb * (nb + 1) / 2;
-            const int r = lane >> 2, c = lane & 3;
-            const double s0 = -sinv[c0 + c], s1 = -sinv[c0 + c + 4];
-            for (int pi = warp; pi < cnt; pi += 8) {
-                int ii = 0, kk = pi;
-                while (kk > ii) { kk -= ii + 1; ii++; }
-                const int I = j + 1 + ii, K = j + 1 + kk;
-                double* cp = Ls + (8 * I + r) * LDT + 8 * K + 2 * c;
-                double2 cv = *reinterpret_cast<double2*>(cp);
-                double acc[2] = {cv.x, cv.y};
-                const double* ap = Ls + (8 * I + r) * LDT + c0 + c;
-                const double* bp = Ls + (8 * K + r) * LDT + c0 + c;
-                dmma884(acc, ap[0] * s0, bp[0]);
-                dmma884(acc, ap[4] * s1, bp[4]);
-                *reinterpret_cast<double2*>(cp) = make_double2(acc[0], acc[1]);
+        const double yk = a[k] * inv[k];
+#pragma unroll
+        for (int c = k + 1; c < 8; c++) a[c] = fma(-yk, GPRN_PT(c, k), a[c]);
+    }
+    if (tid >= c0) {
+        const int u = tid - c0;    // 0..7: row of the diagonal block; >= 8: row below it
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (k == u) {
+                const double p = GPRN_PT(k, k);
+                pivs[tid] = p;
+                sinv[tid] = inv[k];
+                if (!(p > 0.0)) *bad = 1;
             }
-            __syncthreads();
+            Ls[tid * LDT + c0 + k] = a[k];
         }
     }
 #undef GPRN_PT
+}
+
+// C_IK -= T_Ij diag(1/p) T_Kj^T for one 8x8 block (I >= K > j), by one warp, on DMMA m8n8k4
+__device__ __forceinline__ void potrf64_update_block(double* Ls, const double* __restrict__ sinv, int I, int K, int j,
+                                                     int lane) {
+    const int r = lane >> 2, c = lane & 3, c0 = 8 * j;
+    const double s0 = -sinv[c0 + c], s1 = -sinv[c0 + c + 4];
+    double* cp = Ls + (8 * I + r) * LDT + 8 * K + 2 * c;
+    double2 cv = *reinterpret_cast<double2*>(cp);
+    double acc[2] = {cv.x, cv.y};
+    const double* ap = Ls + (8 * I + r) * LDT + c0 + c;
+    const double* bp = Ls + (8 * K + r) * LDT + c0 + c;
+    dmma884(acc, ap[0] * s0, bp[0]);
+    dmma884(acc, ap[4] * s1, bp[4]);
+    *reinterpret_cast<double2*>(cp) = make_double2(acc[0], acc[1]);
+}
+
+// NW: warps of the calling CTA (8: the 256-thread kernels; 4: the 128-thread fused small-N kernel).  Warps 0-1 run
+// phase A, warps 2..NW-1 the rest of the trailing update next to it; the factors do not depend on NW.
+// BAR / tid: the NW warps may be a GROUP of a larger CTA (the fused small-N kernel runs the factorisation on four of
+// its eight warps while the others stream DMMA products): tid is the thread's index inside the group and BAR the
+// named barrier the group synchronises on (0: the whole CTA, __syncthreads).
+template <int BAR, int NTHR>
+__device__ __forceinline__ void group_sync() {
+    if (BAR == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NTHR) : "memory");
+}
+template <int NW, int BAR = 0>
+__device__ __forceinline__ void potrf64_t(const double* Td, int ldd, double* Ls, double* __restrict__ rd,
+                                          double* __restrict__ col, double* __restrict__ pivs, int* bad, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    double* sinv = col;                    // 1 / pivot of the finished columns (64 doubles of the scratch)
+    if (Td != Ls || ldd != LDT) {          // bring the tile into Ls with stride LDT (alias-safe)
+        static_assert(NW == 8 || NW == 4, "potrf64_t: 4 or 8 warps");
+        constexpr int PER = 16 * 8 / NW;   // elements per thread
+        const int r = tid / (NW / 2), q4 = tid % (NW / 2);
+        double a[PER];
+#pragma unroll
+        for (int u = 0; u < PER; u++) a[u] = Td[r * ldd + q4 + (NW / 2) * u];
+        group_sync<BAR, 32 * NW>();
+#pragma unroll
+        for (int u = 0; u < PER; u++) Ls[r * LDT + q4 + (NW / 2) * u] = a[u];
+        group_sync<BAR, 32 * NW>();
+    }
+    if (tid < NB) potrf64_phase_a(Ls, sinv, pivs, bad, 0, tid);
+    group_sync<BAR, 32 * NW>();
+    for (int j = 0; j < 7; j++) {
+        // look-ahead: block column j+1 first (7 - j blocks) ...
+        for (int b = warp; b < 7 - j; b += NW) potrf64_update_block(Ls, sinv, j + 1 + b, j + 1, j, lane);
+        group_sync<BAR, 32 * NW>();
+        if (tid < NB) {
+            potrf64_phase_a(Ls, sinv, pivs, bad, j + 1, tid);                  // ... so that the next step can start
+        } else {
+            // the other warps: the rest of step j, blocks (I, K) with I >= K >= j + 2
+            // (restricting this to the warps that do not share an SM sub-partition with a phase-A warp -- 2, 3, 6, 7 of
+            // eight -- was measured slower: 14.07 k instead of 13.38 k cycles; four warps make it the critical path)
+            const int nb = 6 - j, cnt = nb * (nb + 1) / 2;
+            for (int pi = warp - 2; pi < cnt; pi += NW - 2) {
+                int ii = 0, kk = pi;
+                while (kk > ii) { kk -= ii + 1; ii++; }
+                potrf64_update_block(Ls, sinv, j + 2 + ii, j + 2 + kk, j, lane);
+            }
+        }
+        group_sync<BAR, 32 * NW>();
+    }
     // scale the columns: L[r][c] = T[r][c] / sqrt(p_c), L[c][c] = sqrt(p_c), zeros above the diagonal
     if (tid < NB) rd[tid] = rcp_fast(sqrt(pivs[tid]));
-    __syncthreads();
-    {
-        const int r = tid >> 2, q4 = tid & 3;
+    group_sync<BAR, 32 * NW>();
+    for (int e = tid; e < NB * 4; e += 32 * NW) {
+        const int r = e >> 2, q4 = e & 3;
 #pragma unroll
         for (int u = 0; u < 16; u++) {
             const int cc = q4 + 4 * u;
@@ -354,8 +493,13 @@ __device__ __forceinline__ void potrf64(const double* Td, int ldd, double* Ls, d
             Ls[r * LDT + cc] = v;
         }
     }
-    __syncthreads();
+    group_sync<BAR, 32 * NW>();
 }
+__device__ __forceinline__ void potrf64(const double* Td, int ldd, double* Ls, double* __restrict__ rd,
+                                        double* __restrict__ col, double* __restrict__ pivs, int* bad) {
+    potrf64_t<8>(Td, ldd, Ls, rd, col, pivs, bad, threadIdx.x);
+}
+
 #else
 // potrf64 v1 (-DGPRN_POTRF_V1): tile held in registers (thread (r, q4) owns row r, columns q4 + 4u), outer-product
 // form on UNSCALED columns, one barrier per pivot: the owners of column c+1 publish it to shared memory as soon as

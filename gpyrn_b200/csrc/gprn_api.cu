@@ -214,7 +214,7 @@ static int set_kernel_attrs(int device) {
     CU(cudaFuncSetAttribute(syrk_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM128_SMEM));
     CU(cudaFuncSetAttribute(trtri_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM128_SMEM));
     CU(cudaFuncSetAttribute(trtri_inblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
-    CU(cudaFuncSetAttribute(small_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM));
+    CU(cudaFuncSetAttribute(small_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM + 8192));
     CU(cudaFuncSetAttribute(cross_frob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(predict_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(predict_norm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM128_SMEM));
@@ -556,8 +556,10 @@ static int small_batch(gprn_handle* h, const double* K, const int* d_ids, int nm
     a.K = K; a.ids = d_ids; a.nmat = nmat; a.Np = h->Np; a.dvec = dvec; a.vv = vv;
     a.scratch = scratch; a.uv = uv; a.gv = gv; a.logdet = logdet; a.mstatus = mstatus;
     a.do_inverse = do_inverse;
-    const int grid = std::min(nmat, 2 * h->num_sms);
-    small_pipeline_kernel<<<grid, 256, SMALL_SMEM, st>>>(a);
+    // GPRN_SMALL_CTAS=1 (experiment): one persistent CTA per SM instead of two -- what co-residency buys
+    static const bool one_per_sm = getenv("GPRN_SMALL_CTAS") && atoi(getenv("GPRN_SMALL_CTAS")) == 1;
+    if (one_per_sm) small_pipeline_kernel<<<std::min(nmat, h->num_sms), 256, SMALL_SMEM + 8192, st>>>(a);
+    else small_pipeline_kernel<<<std::min(nmat, SMALL_CTAS_PER_SM * h->num_sms), 256, SMALL_SMEM, st>>>(a);
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -596,8 +598,8 @@ static int setup_engine(gprn_handle* h, int nslot, Engine& E, bool need_factors 
     if (use_small_path(h) && !need_factors) {
         // fused path: factors never reach HBM; a 320 KB scratch per persistent CTA instead (one set of scratch
         // tiles for the iteration kernel, one for the set-up kernel that may run beside it)
-        if (ensure(h->scratch, (size_t)2 * h->num_sms * SMALL_SCRATCH_DOUBLES * sizeof(double))) return 1;
-        if (ensure(h->scratch2, (size_t)2 * h->num_sms * SMALL_SCRATCH_DOUBLES * sizeof(double))) return 1;
+        if (ensure(h->scratch, (size_t)SMALL_CTAS_PER_SM * h->num_sms * SMALL_SCRATCH_DOUBLES * sizeof(double))) return 1;
+        if (ensure(h->scratch2, (size_t)SMALL_CTAS_PER_SM * h->num_sms * SMALL_SCRATCH_DOUBLES * sizeof(double))) return 1;
     } else {
         if (ensure(h->W, matbytes)) return 1;
         // the inverse factors must hold zeros in their (never written) upper tiles: trtri_outer_kernel reads them

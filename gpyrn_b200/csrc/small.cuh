@@ -5,9 +5,18 @@
 // and only the vectors g, u and the scalar log-det leave the chip.  K is read from HBM exactly once
 // (lower tiles); L / X live in a per-CTA scratch of nt(nt+1)/2 tiles -- 10 tiles (320 KB) for Np = 256, which stays
 // L2 resident (296 CTAs x 320 KB = 95 MB < 126 MB L2); 36 tiles (1.15 MB) for Np = 512, which streams through HBM --
-// and X tiles overwrite the L tiles they no longer need.
-// The building blocks are the same as in factor.cuh: DMMA m8n8k4 tile products (mma_tile), the
-// register-resident 64x64 Cholesky (potrf64) and thread-per-vector substitution (subst_lower).
+// and the tiles of the inverse overwrite the L tiles they no longer need.
+//
+// The triangular solves run in the REGISTERS of
+// the warps that hold the right-hand sides as DMMA accumulators (common.cuh: trsm_rows_inreg, shuffles inside a
+// quad + DMMA for the off-diagonal blocks) instead of being staged through shared memory for a thread-per-vector
+// substitution.  For that a 64x64 tile belongs to four warps as 16 x 64 row slabs (mma_slab), and the inverse factor
+// is kept TRANSPOSED in the scratch, Y_ij = X_ij^T: its row sweep  X_ij = -L_ii^-1 sum_k L_ik X_kj  becomes
+//     Y_ij L_ii^T = - sum_{k=j}^{i-1} Y_kj L_ik^T ,      Y_ii L_ii^T = I,
+// the same right-hand solve as the Cholesky panel step  L_ik L_kk^T = A_ik - sum L_ik' L_kk'^T , with both operands
+// of every product read row-major (no transposing loads).  g and z = X v are reduced from the registers
+// (row sums of squares: quad shuffles; column sums: butterfly over the eight row lanes), so the solved tile goes to
+// the scratch once and is never re-read for them.
 // Replaces, for q == 1 and N <= 256 (and for N <= 512 when enough matrices are in flight to give every SM its own:
 // gprn_api.cu: decide_small_path), form_a + panel_col + trtri_* + trmv_* (one launch per phase instead of ~10-70 and
 // none of their HBM round trips).  256 threads: warps 0-3 and 4-7 work on two tiles at a time.
@@ -18,13 +27,8 @@ namespace gprn {
 
 #define SMALL_MAX_NT 8
 #define SMALL_TILES (SMALL_MAX_NT * (SMALL_MAX_NT + 1) / 2)
-#define SMALL_LDV 129              // odd strides: the fused kernel keeps the thread-per-vector substitution
-#ifdef GPRN_POTRF_V1
-#define SMALL_LDP 65               // (measured: the DMMA variant is 11 % slower here, 2 CTAs/SM already hide its latency)
-#else
-#define SMALL_LDP LDT              // potrf64 v2 works in place on the LDT layout
-#endif
 #define SMALL_SCRATCH_DOUBLES (SMALL_TILES * NB * NB)
+#define SMALL_CTAS_PER_SM 2
 // 3 operand tiles + col(128) + pivs(64) + rd(64) + gacc(Np) + zacc(Np): 112 KB, two CTAs per SM
 #define SMALL_SMEM ((3 * NB * LDT + 4 * NB + 2 * SMALL_MAX_NT * NB) * sizeof(double))
 
@@ -61,23 +65,58 @@ __device__ __forceinline__ double* small_tile(double* scratch, int I, int J) {
     return scratch + (size_t)(I * (I + 1) / 2 + J) * (NB * NB);
 }
 
+// slab (accumulator layout) <-> a row-major 64 x 64 tile with leading dimension ld (global scratch: NB, shared: LDT)
+__device__ __forceinline__ void slab_store(const double (&acc)[2][8][2], double* __restrict__ dst, int ld, int w4, int lane) {
+    const int r = lane >> 2, c = lane & 3;
+#pragma unroll
+    for (int x = 0; x < 2; x++)
+#pragma unroll
+        for (int y = 0; y < 8; y++)
+            *reinterpret_cast<double2*>(dst + (size_t)(16 * w4 + 8 * x + r) * ld + 8 * y + 2 * c) = make_double2(acc[x][y][0], acc[x][y][1]);
+}
+__device__ __forceinline__ void slab_load(double (&acc)[2][8][2], const double* __restrict__ src, int ld, int w4, int lane) {
+    const int r = lane >> 2, c = lane & 3;
+#pragma unroll
+    for (int x = 0; x < 2; x++)
+#pragma unroll
+        for (int y = 0; y < 8; y++) {
+            const double2 v = *reinterpret_cast<const double2*>(src + (size_t)(16 * w4 + 8 * x + r) * ld + 8 * y + 2 * c);
+            acc[x][y][0] = v.x;
+            acc[x][y][1] = v.y;
+        }
+}
+
+// slab_load from the L2 scratch (ld.global.cg: the tile was written by OTHER warps of this CTA)
+__device__ __forceinline__ void slab_load_cg(double (&acc)[2][8][2], const double* __restrict__ src, int ld, int w4, int lane) {
+    const int r = lane >> 2, c = lane & 3;
+#pragma unroll
+    for (int x = 0; x < 2; x++)
+#pragma unroll
+        for (int y = 0; y < 8; y++) {
+            const double2 v = __ldcg(reinterpret_cast<const double2*>(src + (size_t)(16 * w4 + 8 * x + r) * ld + 8 * y + 2 * c));
+            acc[x][y][0] = v.x;
+            acc[x][y][1] = v.y;
+        }
+}
+
 __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
     GPRN_TRACE_SCOPE(TK_SMALL);
     extern __shared__ double smem[];
-    double* Bs = smem;                 // B operand / potrf input+output (L_kk) / A operand in the inverse
-    double* As0 = smem + NB * LDT;
-    double* As1 = smem + 2 * NB * LDT;
-    double* V = As0;                   // substitution vectors (stride 129), aliases As0/As1
+    double* Bs = smem;                 // B operand / potrf input + output (L_kk) / L_ii of the solves
+    double* As0 = smem + NB * LDT;     // A operand of warps 0-3; after the products: per-warp column sums (zpart)
+    double* As1 = smem + 2 * NB * LDT; // A operand of warps 4-7; their tile waits here while potrf64 runs
     double* col = smem + 3 * NB * LDT;
     double* pivs = col + 2 * NB;
     double* rd = pivs + NB;
     double* gacc = rd + NB;            // [Np]
     double* zacc = gacc + SMALL_MAX_NT * NB;
+    double* zpart = As0;               // [8 warps][64]
     __shared__ int bad;
     const int Np = a.Np, nt = Np / NB;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int grp = warp >> 2, w4 = warp & 3, wm = w4 >> 1, wn = w4 & 1, tid4 = tid & 127;
+    const int grp = warp >> 2, w4 = warp & 3, tid4 = tid & 127;
     const int r = lane >> 2, c = lane & 3;
+    double* Ag = grp ? As1 : As0;
     double* sc = a.scratch + (size_t)blockIdx.x * SMALL_SCRATCH_DOUBLES;
 #ifdef GPRN_TRACE
     unsigned long long ph_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -95,22 +134,23 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
 
         // ================= Cholesky, left-looking over tile columns =================
         // Column k is done in sub-rounds of two tiles: s = 0 -> (k, k+1), s = 1 -> (k+2, k+3), ...; warps 0-3 take
-        // the first tile of a sub-round, warps 4-7 the second.  One accumulator set is live at a time.
+        // the first tile of a sub-round, warps 4-7 the second.
         for (int k = 0; k < nt; k++) {
             for (int s = 0; k + 2 * s < nt; s++) {
                 const int it = k + 2 * s + grp;
                 const bool have = it < nt;
+                const bool diag = (s == 0 && grp == 0);
                 SMALL_PH(1);
-                double acc[4][4][2];
+                double acc[2][8][2];
 #pragma unroll
-                for (int x = 0; x < 4; x++)
+                for (int x = 0; x < 2; x++)
 #pragma unroll
-                    for (int y = 0; y < 4; y++) {
-                        const int m = wm * 32 + x * 8 + r, n = wn * 32 + y * 8 + 2 * c;
+                    for (int y = 0; y < 8; y++) {
+                        const int m = 16 * w4 + 8 * x + r, n = 8 * y + 2 * c;
                         double2 v = make_double2(0.0, 0.0);
                         if (have) {
                             v = *reinterpret_cast<const double2*>(Km + (size_t)(it * NB + m) * Np + k * NB + n);
-                            if (dv && it == k) {
+                            if (dv && diag) {
                                 if (m == n) v.x += dv[k * NB + m];
                                 if (m == n + 1) v.y += dv[k * NB + m];
                             }
@@ -118,68 +158,59 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
                         acc[x][y][0] = v.x;
                         acc[x][y][1] = v.y;
                     }
-                const bool diag = (s == 0 && grp == 0);
+                {   // the K tile of this group's NEXT sub-round goes to L2 now: its HBM latency hides behind this round
+                    int kn = k, sn = s + 1;
+                    if (k + 2 * sn >= nt) { kn = k + 1; sn = 0; }
+                    const int itn = kn + 2 * sn + grp;
+                    if (kn < nt && itn < nt) {
+                        const double* nx = Km + (size_t)(itn * NB + (tid4 >> 1)) * Np + kn * NB + (tid4 & 1) * 32;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 16));
+                    }
+                }
                 SMALL_PH(2);
                 for (int kp = 0; kp < k; kp++) {
                     load_tile<false, false>(Bs, small_tile(sc, k, kp), NB, tid, 256);
-                    if (have && !diag) load_tile<false, false>(grp ? As1 : As0, small_tile(sc, it, kp), NB, tid4, 128);
+                    if (have && !diag) load_tile<false, false>(Ag, small_tile(sc, it, kp), NB, tid4, 128);
                     cp_async_commit();
                     cp_async_wait<0>();
                     __syncthreads();
-                    if (have) mma_tile<true>(acc, diag ? Bs : (grp ? As1 : As0), Bs, wm, wn, lane);
+                    if (have) mma_slab<true>(acc, diag ? Bs : Ag, Bs, w4, lane);
                     __syncthreads();
                 }
                 SMALL_PH(3);
                 if (s == 0) {
-#pragma unroll
-                    for (int x = 0; x < 4; x++)
-#pragma unroll
-                        for (int y = 0; y < 4; y++) {
-                            const int m = wm * 32 + x * 8 + r, n = wn * 32 + y * 8 + 2 * c;
-                            if (grp == 0) {
-                                Bs[m * SMALL_LDP + n] = acc[x][y][0];
-                                Bs[m * SMALL_LDP + n + 1] = acc[x][y][1];
-                            } else if (have) {
-                                V[n * SMALL_LDV + NB + m] = acc[x][y][0];
-                                V[(n + 1) * SMALL_LDV + NB + m] = acc[x][y][1];
-                            }
-                        }
+                    // the diagonal tile goes to Bs for potrf64; the tile below it waits in As1 (its accumulators
+                    // would not survive the register demand of the factorisation)
+                    if (grp == 0) slab_store(acc, Bs, LDT, w4, lane);
+                    else if (have) slab_store(acc, As1, LDT, w4, lane);
                     __syncthreads();
                     SMALL_PH(4);
-                    potrf64(Bs, SMALL_LDP, Bs, rd, col, pivs, &bad);
+                    potrf64(Bs, LDT, Bs, rd, col, pivs, &bad);
                     SMALL_PH(5);
-                    if (tid >= NB && tid < 2 * NB && k + 1 < nt) subst_lower(Bs, LDT, rd, V, SMALL_LDV, tid);
                     if (tid < 32) logsum += log(pivs[tid]) + log(pivs[tid + 32]);
-                    __syncthreads();
-                    SMALL_PH(6);
-                    double* dkk = small_tile(sc, k, k);
-                    for (int e = tid; e < NB * NB; e += 256) dkk[e] = Bs[(e >> 6) * LDT + (e & 63)];
-                    if (k + 1 < nt) {
-                        double* d1 = small_tile(sc, k + 1, k);
-                        for (int e = tid; e < NB * NB; e += 256) d1[e] = V[(e & 63) * SMALL_LDV + NB + (e >> 6)];
+                    if (grp == 0) {
+                        double* dkk = small_tile(sc, k, k);
+                        for (int e = tid4; e < NB * (NB / 2); e += 128) {
+                            const int m = e >> 5, c2 = e & 31;
+                            *reinterpret_cast<double2*>(dkk + m * NB + 2 * c2) = *reinterpret_cast<const double2*>(Bs + m * LDT + 2 * c2);
+                        }
+                    } else if (have) {
+                        slab_load(acc, As1, LDT, w4, lane);
+                        trsm_rows_inreg(acc, Bs, rd, lane);
+                        SMALL_PH(6);
+                        slab_store(acc, small_tile(sc, it, k), NB, w4, lane);
                     }
                 } else {
-#pragma unroll
-                    for (int x = 0; x < 4; x++)
-#pragma unroll
-                        for (int y = 0; y < 4; y++) {
-                            const int m = wm * 32 + x * 8 + r, n = wn * 32 + y * 8 + 2 * c;
-                            if (have) {
-                                V[n * SMALL_LDV + grp * NB + m] = acc[x][y][0];
-                                V[(n + 1) * SMALL_LDV + grp * NB + m] = acc[x][y][1];
-                            }
-                        }
                     load_tile<false>(Bs, small_tile(sc, k, k), NB, tid, 256);     // L_kk back from the scratch
                     __syncthreads();
                     if (tid < NB) rd[tid] = 1.0 / Bs[tid * LDT + tid];
                     __syncthreads();
                     SMALL_PH(5);
-                    if (tid < 2 * NB && k + 2 + (tid >> 6) < nt) subst_lower(Bs, LDT, rd, V, SMALL_LDV, tid);
-                    __syncthreads();
-                    SMALL_PH(6);
                     if (have) {
-                        double* d2 = small_tile(sc, it, k);
-                        for (int e = tid4; e < NB * NB; e += 128) d2[e] = V[(e & 63) * SMALL_LDV + grp * NB + (e >> 6)];
+                        trsm_rows_inreg(acc, Bs, rd, lane);
+                        SMALL_PH(6);
+                        slab_store(acc, small_tile(sc, it, k), NB, w4, lane);
                     }
                 }
                 __syncthreads();
@@ -195,8 +226,8 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
         SMALL_PH(0);
         if (!a.do_inverse) continue;
 
-        // ================= inverse by block rows; X tiles overwrite the L tiles =================
-        const double* vglob = a.vv + (size_t)id * Np;      // right-hand side v: broadcast reads, L1 / L2 resident
+        // ================= inverse by block rows, transposed: Y_ij = X_ij^T overwrites L_ij =================
+        const double* vglob = a.vv + (size_t)id * Np;
         for (int e = tid; e < Np; e += 256) {
             gacc[e] = 0.0;
             zacc[e] = 0.0;
@@ -204,81 +235,109 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
         __syncthreads();
         for (int i = 0; i < nt; i++) {
             for (int j0 = 0; j0 <= i; j0 += 2) {
-                const int j = j0 + grp;                 // this group's right-hand-side tile (j == i: identity)
+                const int j = j0 + grp;                 // this group's column tile (j == i: identity right-hand side)
+                const bool act = j <= i;
                 SMALL_PH(7);
-                double acc[4][4][2];
+                double acc[2][8][2];
 #pragma unroll
-                for (int x = 0; x < 4; x++)
+                for (int x = 0; x < 2; x++)
 #pragma unroll
-                    for (int y = 0; y < 4; y++) acc[x][y][0] = acc[x][y][1] = 0.0;
+                    for (int y = 0; y < 8; y++) acc[x][y][0] = acc[x][y][1] = 0.0;
                 for (int k = j0; k < i; k++) {
-                    load_tile<false, false>(Bs, small_tile(sc, i, k), NB, tid, 256);                // L_ik (shared A operand)
+                    load_tile<false, false>(Bs, small_tile(sc, i, k), NB, tid, 256);              // L_ik   (B operand)
                     const bool part = (j < i) && (k >= j);
-                    if (part) load_tile<true, false>(grp ? As1 : As0, small_tile(sc, k, j), NB, tid4, 128);   // X_kj^T
+                    if (part) load_tile<false, false>(Ag, small_tile(sc, k, j), NB, tid4, 128);   // Y_kj   (A operand)
                     cp_async_commit();
                     cp_async_wait<0>();
                     __syncthreads();
-                    if (part) mma_tile<true>(acc, Bs, grp ? As1 : As0, wm, wn, lane);
+                    if (part) mma_slab<true>(acc, Ag, Bs, w4, lane);                              // - sum Y_kj L_ik^T
                     __syncthreads();
                 }
                 SMALL_PH(8);
-                // stage right-hand sides: vector = column n of the tile, element m at V[m*ldv + grp*64 + n]
-                if (j < i) {
+                if (j == i) {
 #pragma unroll
-                    for (int x = 0; x < 4; x++)
+                    for (int x = 0; x < 2; x++)
 #pragma unroll
-                        for (int y = 0; y < 4; y++) {
-                            const int m = wm * 32 + x * 8 + r, n = wn * 32 + y * 8 + 2 * c;
-                            V[m * SMALL_LDV + grp * NB + n] = acc[x][y][0];
-                            V[m * SMALL_LDV + grp * NB + n + 1] = acc[x][y][1];
+                        for (int y = 0; y < 8; y++) {
+                            const int n = 16 * w4 + 8 * x + r, m = 8 * y + 2 * c;
+                            acc[x][y][0] = (n == m) ? 1.0 : 0.0;
+                            acc[x][y][1] = (n == m + 1) ? 1.0 : 0.0;
                         }
-                } else if (j == i) {
-                    for (int e = tid4; e < NB * NB; e += 128) V[(e >> 6) * SMALL_LDV + grp * NB + (e & 63)] = ((e >> 6) == (e & 63)) ? 1.0 : 0.0;
                 }
-                load_tile<false>(Bs, small_tile(sc, i, i), NB, tid, 256);                           // L_ii
+                load_tile<false>(Bs, small_tile(sc, i, i), NB, tid, 256);                         // L_ii
                 __syncthreads();
                 if (tid < NB) rd[tid] = 1.0 / Bs[tid * LDT + tid];
                 __syncthreads();
-                const int jt = j0 + (tid >> 6);          // tile handled by thread tid < 128 in the substitution
                 SMALL_PH(9);
-                if (tid < 2 * NB && jt <= i) subst_lower(Bs, LDT, rd, V, SMALL_LDV, tid, jt == i ? ((tid & 63) >> 3) : 0);
-                __syncthreads();
-                SMALL_PH(10);
-                if (tid < 2 * NB && jt <= i) {
-                    // column sums of squares of X_ij (thread = column) -> g_j ; single writer per (j, n) and round
-                    double sg = 0.0;
-                    for (int m = 0; m < NB; m++) { double x = V[m * SMALL_LDV + tid]; sg = fma(x, x, sg); }
-                    gacc[jt * NB + (tid & 63)] += sg;
-                }
-                if (tid >= 2 * NB && tid < 3 * NB) {
-                    // row sums X_ij v_j (thread = row) -> z_i ; one thread adds both tiles of the round (fixed order)
-                    const int m = tid - 2 * NB;
-                    double sz = 0.0;
-                    for (int g2 = 0; g2 < 2; g2++) {
-                        const int jj = j0 + g2;
-                        if (jj <= i)
-                            for (int n = 0; n < NB; n++) sz = fma(V[m * SMALL_LDV + g2 * NB + n], vglob[jj * NB + n], sz);
+                if (act) {
+                    trsm_rows_inreg(acc, Bs, rd, lane, j == i ? 2 * w4 : 0);
+                    SMALL_PH(10);
+                    // g_j[n] += sum_m Y_ij[n][m]^2 : the four lanes of a quad hold one row
+                    double vn[2];
+#pragma unroll
+                    for (int x = 0; x < 2; x++) {
+                        double sg = 0.0;
+#pragma unroll
+                        for (int y = 0; y < 8; y++) {
+                            sg = fma(acc[x][y][0], acc[x][y][0], sg);
+                            sg = fma(acc[x][y][1], acc[x][y][1], sg);
+                        }
+                        sg += __shfl_xor_sync(0xffffffffu, sg, 1);
+                        sg += __shfl_xor_sync(0xffffffffu, sg, 2);
+                        const int n = 16 * w4 + 8 * x + r;
+                        if (c == 0) gacc[j * NB + n] += sg;          // single writer per (j, n) and round
+                        vn[x] = vglob[j * NB + n];
                     }
-                    zacc[i * NB + m] += sz;
+                    // z_i[m] += sum_n Y_ij[n][m] v_j[n] : per-warp column sums (butterfly over the row lanes)
+#pragma unroll
+                    for (int y = 0; y < 8; y++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            double t = acc[0][y][e] * vn[0];
+                            t = fma(acc[1][y][e], vn[1], t);
+                            t += __shfl_xor_sync(0xffffffffu, t, 4);
+                            t += __shfl_xor_sync(0xffffffffu, t, 8);
+                            t += __shfl_xor_sync(0xffffffffu, t, 16);
+                            if (r == 0) zpart[warp * NB + 8 * y + 2 * c + e] = t;
+                        }
+                    slab_store(acc, small_tile(sc, i, j), NB, w4, lane);
                 }
-                if (j <= i) {
-                    double* dx = small_tile(sc, i, j);
-                    for (int e = tid4; e < NB * NB; e += 128) dx[e] = V[(e >> 6) * SMALL_LDV + grp * NB + (e & 63)];
+                __syncthreads();
+                if (tid < NB) {        // fixed order: the four slabs of the first tile, then those of the second
+                    double t = (zpart[tid] + zpart[NB + tid]) + (zpart[2 * NB + tid] + zpart[3 * NB + tid]);
+                    if (j0 + 1 <= i) t += (zpart[4 * NB + tid] + zpart[5 * NB + tid]) + (zpart[6 * NB + tid] + zpart[7 * NB + tid]);
+                    zacc[i * NB + tid] += t;
                 }
                 __syncthreads();
             }
         }
         SMALL_PH(11);
-        // u_j[n] = sum_{i >= j} sum_m X_ij[m][n] z_i[m]   (X tiles from the scratch)
-        for (int e = tid; e < Np; e += 256) {
-            const int j = e >> 6, n = e & 63;
-            double su = 0.0;
-            for (int i = j; i < nt; i++) {
-                const double* xt = small_tile(sc, i, j);
-                for (int m = 0; m < NB; m++) su = fma(xt[m * NB + n], zacc[i * NB + m], su);
+        // u_j[n] = sum_{i >= j} sum_m Y_ij[n][m] z_i[m] : thread = (row n, quarter of the row), eight independent
+        // 16-byte loads in flight per thread and tile (the tiles come from the L2 scratch); the four quarters of a
+        // row are combined by quad shuffles
+        {
+            const int n = tid >> 2, qd = tid & 3;
+            for (int j = 0; j < nt; j++) {
+                double su = 0.0;
+                for (int i = j; i < nt; i++) {
+                    const double* yrow = small_tile(sc, i, j) + n * NB + qd * 16;
+                    const double* zi = zacc + i * NB + qd * 16;
+                    double2 v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) v[e] = *reinterpret_cast<const double2*>(yrow + 2 * e);
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        su = fma(v[e].x, zi[2 * e], su);
+                        su = fma(v[e].y, zi[2 * e + 1], su);
+                    }
+                }
+                su += __shfl_xor_sync(0xffffffffu, su, 1);
+                su += __shfl_xor_sync(0xffffffffu, su, 2);
+                if (qd == 0) {
+                    a.uv[(size_t)id * Np + j * NB + n] = su;
+                    a.gv[(size_t)id * Np + j * NB + n] = gacc[j * NB + n];
+                }
             }
-            a.uv[(size_t)id * Np + e] = su;
-            a.gv[(size_t)id * Np + e] = gacc[e];
         }
         __syncthreads();
         SMALL_PH(0);
