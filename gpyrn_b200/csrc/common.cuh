@@ -42,6 +42,44 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// ------------------------------------------------------------------------------------------------
+// TMA bulk copies (cp.async.bulk, SASS: UBLKCP) completing on an mbarrier: one warp moves a 64x64 tile as 64 row
+// copies of 512 bytes -- each lane issues two -- instead of every thread of the CTA computing addresses for eight
+// 16-byte LDGSTS, and the threads that consume the tile wait on the mbarrier's phase instead of on a CTA barrier.
+// The destination keeps the padded row stride LDT (a 1-D bulk copy cannot swizzle; the pad is what keeps the m8n8k4
+// fragment loads conflict-free).  Data written with ordinary stores that a bulk copy reads or overwrites (scratch
+// tiles in global memory, operand buffers in shared memory) needs fence_proxy_async() between the two proxies.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Wait for the phase with the given parity.  Bounded: a protocol error becomes a flagged result, not a hung GPU.
+__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned parity) {
+    for (int i = 0; i < (1 << 24); i++) {
+        unsigned ok;
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+// One warp issues the 64 row copies of a tile (row-major source with leading dimension ld doubles -> dst[64][LDT]).
+__device__ __forceinline__ void load_tile_bulk(double* dst, const double* __restrict__ src, size_t ld, int lane,
+                                               unsigned long long* bar) {
+    bulk_g2s(dst + lane * LDT, src + (size_t)lane * ld, NB * sizeof(double), bar);
+    bulk_g2s(dst + (lane + 32) * LDT, src + (size_t)(lane + 32) * ld, NB * sizeof(double), bar);
+}
+
 // Load a 64x64 tile from global memory (row-major, leading dimension ld) into shared memory
 // dst[64][LDT].  TRANS: dst[m][k] = src[k*ld + m].  All `nthreads` threads of the CTA call.
 // The copy is issued as cp.async (every element of the tile is in flight at once: one memory round trip per tile

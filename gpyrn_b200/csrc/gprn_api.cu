@@ -214,7 +214,8 @@ static int set_kernel_attrs(int device) {
     CU(cudaFuncSetAttribute(syrk_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM128_SMEM));
     CU(cudaFuncSetAttribute(trtri_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM128_SMEM));
     CU(cudaFuncSetAttribute(trtri_inblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
-    CU(cudaFuncSetAttribute(small_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM + 8192));
+    CU(cudaFuncSetAttribute(small_pipeline_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM + 8192));
+    CU(cudaFuncSetAttribute(small_pipeline_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM + 8192));
     CU(cudaFuncSetAttribute(cross_frob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(predict_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(predict_norm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM128_SMEM));
@@ -558,8 +559,12 @@ static int small_batch(gprn_handle* h, const double* K, const int* d_ids, int nm
     a.do_inverse = do_inverse;
     // GPRN_SMALL_CTAS=1 (experiment): one persistent CTA per SM instead of two -- what co-residency buys
     static const bool one_per_sm = getenv("GPRN_SMALL_CTAS") && atoi(getenv("GPRN_SMALL_CTAS")) == 1;
-    if (one_per_sm) small_pipeline_kernel<<<std::min(nmat, h->num_sms), 256, SMALL_SMEM + 8192, st>>>(a);
-    else small_pipeline_kernel<<<std::min(nmat, SMALL_CTAS_PER_SM * h->num_sms), 256, SMALL_SMEM, st>>>(a);
+    // GPRN_SMALL_NO_TMA=1: tile loads as per-thread cp.async copies instead of TMA bulk copies (A/B switch)
+    static const bool no_tma = getenv("GPRN_SMALL_NO_TMA") != nullptr;
+    const int grid = one_per_sm ? std::min(nmat, h->num_sms) : std::min(nmat, SMALL_CTAS_PER_SM * h->num_sms);
+    const size_t smem = SMALL_SMEM + (one_per_sm ? 8192 : 0);
+    if (no_tma) small_pipeline_kernel<false><<<grid, 256, smem, st>>>(a);
+    else small_pipeline_kernel<true><<<grid, 256, smem, st>>>(a);
     LAUNCH_CHECK(h);
     return 0;
 }

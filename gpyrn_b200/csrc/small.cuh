@@ -27,7 +27,11 @@ namespace gprn {
 
 #define SMALL_MAX_NT 8
 #define SMALL_TILES (SMALL_MAX_NT * (SMALL_MAX_NT + 1) / 2)
-#define SMALL_SCRATCH_DOUBLES (SMALL_TILES * NB * NB)
+// scratch tiles keep the padded row stride of the shared-memory operand tiles (LDT), so that ONE TMA bulk copy moves a
+// tile verbatim into an operand buffer
+#define SMALL_LDS LDT
+#define SMALL_TILE_DOUBLES (NB * SMALL_LDS)
+#define SMALL_SCRATCH_DOUBLES (SMALL_TILES * SMALL_TILE_DOUBLES)
 #define SMALL_CTAS_PER_SM 2
 // 3 operand tiles + col(128) + pivs(64) + rd(64) + gacc(Np) + zacc(Np): 112 KB, two CTAs per SM
 #define SMALL_SMEM ((3 * NB * LDT + 4 * NB + 2 * SMALL_MAX_NT * NB) * sizeof(double))
@@ -62,7 +66,7 @@ struct SmallArgs {
 };
 
 __device__ __forceinline__ double* small_tile(double* scratch, int I, int J) {
-    return scratch + (size_t)(I * (I + 1) / 2 + J) * (NB * NB);
+    return scratch + (size_t)(I * (I + 1) / 2 + J) * SMALL_TILE_DOUBLES;
 }
 
 // slab (accumulator layout) <-> a row-major 64 x 64 tile with leading dimension ld (global scratch: NB, shared: LDT)
@@ -99,6 +103,36 @@ __device__ __forceinline__ void slab_load_cg(double (&acc)[2][8][2], const doubl
         }
 }
 
+// One load round of the kernel: the B tile (all warps) and up to two A tiles (one per warp group) from the scratch.
+// TMA: thread 0 issues one bulk copy per tile (34 816 bytes) on the mbarrier and every thread waits for the phase; otherwise each
+// thread issues its share as 16-byte cp.async copies and the CTA meets at a barrier.  The caller guarantees (by the
+// barrier that ended the previous use) that nobody still reads the destination buffers.
+template <bool TMA>
+__device__ __forceinline__ void small_load_round(double* Bs, const double* srcB, double* A0, const double* srcA0,
+                                                 double* A1, const double* srcA1, int tid, unsigned long long* bar,
+                                                 unsigned& phase, int* bad) {
+    if (TMA) {
+        if (tid == 0) {
+            constexpr unsigned TB = (unsigned)(SMALL_TILE_DOUBLES * sizeof(double));
+            fence_proxy_async();
+            mbar_expect_tx(bar, TB * (1u + (srcA0 != nullptr) + (srcA1 != nullptr)));
+            bulk_g2s(Bs, srcB, TB, bar);
+            if (srcA0) bulk_g2s(A0, srcA0, TB, bar);
+            if (srcA1) bulk_g2s(A1, srcA1, TB, bar);
+        }
+        if (!mbar_wait(bar, phase)) *bad = 2;
+        phase ^= 1u;
+    } else {
+        load_tile<false, false>(Bs, srcB, SMALL_LDS, tid, 256);
+        if (tid < 128) { if (srcA0) load_tile<false, false>(A0, srcA0, SMALL_LDS, tid, 128); }
+        else if (srcA1) load_tile<false, false>(A1, srcA1, SMALL_LDS, tid - 128, 128);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+}
+
+template <bool TMA>
 __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
     GPRN_TRACE_SCOPE(TK_SMALL);
     extern __shared__ double smem[];
@@ -112,12 +146,18 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
     double* zacc = gacc + SMALL_MAX_NT * NB;
     double* zpart = As0;               // [8 warps][64]
     __shared__ int bad;
+    __shared__ unsigned long long tma_bar;          // mbarrier of the bulk tile loads (one phase per load round)
+    unsigned phase = 0;
     const int Np = a.Np, nt = Np / NB;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int grp = warp >> 2, w4 = warp & 3, tid4 = tid & 127;
     const int r = lane >> 2, c = lane & 3;
     double* Ag = grp ? As1 : As0;
     double* sc = a.scratch + (size_t)blockIdx.x * SMALL_SCRATCH_DOUBLES;
+    if (TMA) {
+        if (tid == 0) mbar_init(&tma_bar, 1);
+        __syncthreads();
+    }
 #ifdef GPRN_TRACE
     unsigned long long ph_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long ph_last = clock64();
@@ -170,11 +210,9 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
                 }
                 SMALL_PH(2);
                 for (int kp = 0; kp < k; kp++) {
-                    load_tile<false, false>(Bs, small_tile(sc, k, kp), NB, tid, 256);
-                    if (have && !diag) load_tile<false, false>(Ag, small_tile(sc, it, kp), NB, tid4, 128);
-                    cp_async_commit();
-                    cp_async_wait<0>();
-                    __syncthreads();
+                    const int it0 = k + 2 * s;           // tile of warps 0-3 (the diagonal one when s == 0), it0 + 1: warps 4-7
+                    small_load_round<TMA>(Bs, small_tile(sc, k, kp), As0, s > 0 ? small_tile(sc, it0, kp) : nullptr,
+                                          As1, it0 + 1 < nt ? small_tile(sc, it0 + 1, kp) : nullptr, tid, &tma_bar, phase, &bad);
                     if (have) mma_slab<true>(acc, diag ? Bs : Ag, Bs, w4, lane);
                     __syncthreads();
                 }
@@ -193,24 +231,26 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
                         double* dkk = small_tile(sc, k, k);
                         for (int e = tid4; e < NB * (NB / 2); e += 128) {
                             const int m = e >> 5, c2 = e & 31;
-                            *reinterpret_cast<double2*>(dkk + m * NB + 2 * c2) = *reinterpret_cast<const double2*>(Bs + m * LDT + 2 * c2);
+                            *reinterpret_cast<double2*>(dkk + m * SMALL_LDS + 2 * c2) = *reinterpret_cast<const double2*>(Bs + m * LDT + 2 * c2);
                         }
+                        if (TMA) fence_proxy_async();
                     } else if (have) {
                         slab_load(acc, As1, LDT, w4, lane);
                         trsm_rows_inreg(acc, Bs, rd, lane);
                         SMALL_PH(6);
-                        slab_store(acc, small_tile(sc, it, k), NB, w4, lane);
+                        slab_store(acc, small_tile(sc, it, k), SMALL_LDS, w4, lane);
+                        if (TMA) fence_proxy_async();
                     }
                 } else {
-                    load_tile<false>(Bs, small_tile(sc, k, k), NB, tid, 256);     // L_kk back from the scratch
-                    __syncthreads();
+                    small_load_round<TMA>(Bs, small_tile(sc, k, k), nullptr, nullptr, nullptr, nullptr, tid, &tma_bar, phase, &bad);   // L_kk back
                     if (tid < NB) rd[tid] = 1.0 / Bs[tid * LDT + tid];
                     __syncthreads();
                     SMALL_PH(5);
                     if (have) {
                         trsm_rows_inreg(acc, Bs, rd, lane);
                         SMALL_PH(6);
-                        slab_store(acc, small_tile(sc, it, k), NB, w4, lane);
+                        slab_store(acc, small_tile(sc, it, k), SMALL_LDS, w4, lane);
+                        if (TMA) fence_proxy_async();
                     }
                 }
                 __syncthreads();
@@ -244,12 +284,10 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
 #pragma unroll
                     for (int y = 0; y < 8; y++) acc[x][y][0] = acc[x][y][1] = 0.0;
                 for (int k = j0; k < i; k++) {
-                    load_tile<false, false>(Bs, small_tile(sc, i, k), NB, tid, 256);              // L_ik   (B operand)
                     const bool part = (j < i) && (k >= j);
-                    if (part) load_tile<false, false>(Ag, small_tile(sc, k, j), NB, tid4, 128);   // Y_kj   (A operand)
-                    cp_async_commit();
-                    cp_async_wait<0>();
-                    __syncthreads();
+                    // L_ik (B operand of both groups) and the groups' A operands Y_k,j0 / Y_k,j0+1
+                    small_load_round<TMA>(Bs, small_tile(sc, i, k), As0, small_tile(sc, k, j0),
+                                          As1, (j0 + 1 < i && k >= j0 + 1) ? small_tile(sc, k, j0 + 1) : nullptr, tid, &tma_bar, phase, &bad);
                     if (part) mma_slab<true>(acc, Ag, Bs, w4, lane);                              // - sum Y_kj L_ik^T
                     __syncthreads();
                 }
@@ -264,8 +302,7 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
                             acc[x][y][1] = (n == m + 1) ? 1.0 : 0.0;
                         }
                 }
-                load_tile<false>(Bs, small_tile(sc, i, i), NB, tid, 256);                         // L_ii
-                __syncthreads();
+                small_load_round<TMA>(Bs, small_tile(sc, i, i), nullptr, nullptr, nullptr, nullptr, tid, &tma_bar, phase, &bad);   // L_ii
                 if (tid < NB) rd[tid] = 1.0 / Bs[tid * LDT + tid];
                 __syncthreads();
                 SMALL_PH(9);
@@ -300,7 +337,8 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
                             t += __shfl_xor_sync(0xffffffffu, t, 16);
                             if (r == 0) zpart[warp * NB + 8 * y + 2 * c + e] = t;
                         }
-                    slab_store(acc, small_tile(sc, i, j), NB, w4, lane);
+                    slab_store(acc, small_tile(sc, i, j), SMALL_LDS, w4, lane);
+                    if (TMA) fence_proxy_async();
                 }
                 __syncthreads();
                 if (tid < NB) {        // fixed order: the four slabs of the first tile, then those of the second
@@ -320,7 +358,7 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
             for (int j = 0; j < nt; j++) {
                 double su = 0.0;
                 for (int i = j; i < nt; i++) {
-                    const double* yrow = small_tile(sc, i, j) + n * NB + qd * 16;
+                    const double* yrow = small_tile(sc, i, j) + n * SMALL_LDS + qd * 16;
                     const double* zi = zacc + i * NB + qd * 16;
                     double2 v[8];
 #pragma unroll
