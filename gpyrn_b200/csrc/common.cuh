@@ -188,6 +188,49 @@ __device__ __forceinline__ void mma_slab(double (&acc)[2][8][2], const double* _
     }
 }
 
+// As mma_slab, with the A fragments read STRAIGHT FROM GLOBAL MEMORY (Ag: the 64 x 64 A tile, row-major, leading
+// dimension lda; it sits in the L2-resident scratch): a lane's fragment element A[row][4 ks + c] is an 8-byte load, a
+// quad reads one 32-byte sector, and every element is used by exactly one lane -- staging the A tile in shared memory
+// would only add a copy.  The loads run a chunk of four k-steps (64 DMMAs, ~1000 cycles) ahead of their use, which
+// covers the L2 latency.  Only the B tile (read by all four warps) needs shared memory.
+template <bool NEG>
+__device__ __forceinline__ void mma_slab_ga(double (&acc)[2][8][2], const double* __restrict__ Ag, int lda,
+                                            const double* __restrict__ Bs, int w4, int lane) {
+    const int r = lane >> 2, c = lane & 3;
+    const double* ap = Ag + (size_t)(w4 * 16 + r) * lda + c;
+    const double* bp = Bs + r * LDT + c;
+    double an[4][2];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int x = 0; x < 2; x++) an[u][x] = __ldcg(ap + (size_t)x * 8 * lda + 4 * u);
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) {
+        double ac[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int x = 0; x < 2; x++) ac[u][x] = NEG ? -an[u][x] : an[u][x];
+        if (ch < 3) {
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int x = 0; x < 2; x++) an[u][x] = __ldcg(ap + (size_t)x * 8 * lda + 16 * (ch + 1) + 4 * u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k0 = 16 * ch + 4 * u;
+            double b[8];
+#pragma unroll
+            for (int y = 0; y < 8; y++) b[y] = bp[y * 8 * LDT + k0];
+#pragma unroll
+            for (int x = 0; x < 2; x++)
+#pragma unroll
+                for (int y = 0; y < 8; y++) dmma884(acc[x][y], ac[u][x], b[y]);
+        }
+    }
+}
+
 // Solve  X L^T = T  in place for the warp's slab (forward substitution along the columns, right-looking over the
 // eight 8-column blocks).  Ls: L, 64 x 64 lower triangular in shared memory (stride LDT); rd[j] = 1 / L[j][j].
 // Block step y:  (a) the 8 x 8 diagonal block is solved inside each quad (the four lanes of a quad hold one row's

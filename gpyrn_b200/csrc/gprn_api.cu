@@ -13,6 +13,7 @@
 #include "assemble.cuh"
 #include "factor.cuh"
 #include "small.cuh"
+#include "mid.cuh"
 #include "elbo.cuh"
 #include "predict.cuh"
 
@@ -101,6 +102,7 @@ struct gprn_handle {
     bool model_set = false;
     bool capturing = false;                     // inside a stream capture (CUDA graph of one iteration)
     bool small_mode = false;                    // this call runs the fused small-N pipeline (decide_small_path)
+    bool mid_mode = false;                      // this call runs the multi-CTA dataflow pipeline (decide_mid_path)
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // stream groups: set 0 for the fixed-point iteration, set 1 for the set-up of newly admitted sets, which runs
@@ -126,7 +128,7 @@ struct gprn_handle {
     std::vector<int32_t> h_tok, h_len, h_par_off, h_npar;
     // workspace (grow only)
     std::vector<DevBuf*> all;
-    DevBuf K, W, X, XK, vecs, state, small, lists, rlist, hyper, ysub, ks, pred, scratch, scratch2, gpart, res, kscratch;
+    DevBuf K, W, X, XK, vecs, state, small, lists, rlist, hyper, ysub, ks, pred, scratch, scratch2, gpart, res, kscratch, mid_state, mid_zp, mid_ld;
     ChainStore chain;         // user-visible store (gprn_chain_*)
     ChainStore tmp_chain;     // backing of mu_inout / var_inout of gprn_elbo_batched
     int num_sms = 148;
@@ -153,6 +155,15 @@ static bool decide_small_path(const gprn_handle* h, int64_t sets_in_flight) {
     static const int max_nt = getenv("GPRN_SMALL_MAX_NT") ? atoi(getenv("GPRN_SMALL_MAX_NT")) : SMALL_MAX_NT;
     if (h->q != 1 || h->nt > std::min(max_nt, SMALL_MAX_NT) || getenv("GPRN_NO_SMALL") != nullptr) return false;
     return h->nt <= 4 || sets_in_flight * h->M >= 2 * (int64_t)h->num_sms;
+}
+
+// Latency path (mid.cuh): q == 1, N <= 512 and so few matrices in flight that every CTA of a launch (nt per matrix)
+// is resident at once -- a single ELBOcalc, a handful of walkers.  One matrix is then worked on by nt CTAs coupled by
+// tile flags instead of by one CTA (small.cuh) or ~20 dependent launches (factor.cuh).  GPRN_NO_MID=1 disables it.
+static bool use_mid_path(const gprn_handle* h) { return h->mid_mode; }
+static bool decide_mid_path(const gprn_handle* h, int64_t sets_in_flight) {
+    if (h->q != 1 || h->nt > MID_MAX_NT || getenv("GPRN_NO_MID") != nullptr) return false;
+    return sets_in_flight * h->M * h->nt <= 2 * (int64_t)h->num_sms;
 }
 
 static void drop_graphs(gprn_handle* h) {
@@ -216,6 +227,7 @@ static int set_kernel_attrs(int device) {
     CU(cudaFuncSetAttribute(trtri_inblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
     CU(cudaFuncSetAttribute(small_pipeline_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM + 8192));
     CU(cudaFuncSetAttribute(small_pipeline_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM + 8192));
+    CU(cudaFuncSetAttribute(mid_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM));
     CU(cudaFuncSetAttribute(cross_frob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(predict_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(predict_norm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM128_SMEM));
@@ -286,7 +298,7 @@ extern "C" int gprn_create(int device, int N, int p, int q, const double* time, 
     CU(cudaMemcpy(h->d_ysub_shared, y, sizeof(double) * p * N, cudaMemcpyHostToDevice));
     CU(cudaDeviceSynchronize());   // pageable-memory copies above must have landed before any non-blocking stream runs
     h->all = {&h->K, &h->W, &h->X, &h->XK, &h->vecs, &h->state, &h->small, &h->lists, &h->rlist, &h->hyper, &h->ysub,
-              &h->ks, &h->pred, &h->scratch, &h->scratch2, &h->gpart, &h->res, &h->kscratch,
+              &h->ks, &h->pred, &h->scratch, &h->scratch2, &h->gpart, &h->res, &h->kscratch, &h->mid_state, &h->mid_zp, &h->mid_ld,
               &h->chain.mu, &h->chain.var, &h->chain.valid, &h->tmp_chain.mu, &h->tmp_chain.var, &h->tmp_chain.valid};
     *out = h;
     return 0;
@@ -569,6 +581,30 @@ static int small_batch(gprn_handle* h, const double* K, const int* d_ids, int nm
     return 0;
 }
 
+// Clears the tile flags of the listed matrices (the set-up of new sets may run beside an iteration: each launch only
+// touches its own matrices).  grid = (nmat), block = 64.
+__global__ void mid_clear_kernel(int* __restrict__ tstate, const int* __restrict__ ids) {
+    if (threadIdx.x < MID_TILES) tstate[(size_t)ids[blockIdx.x] * MID_TILES + threadIdx.x] = 0;
+}
+
+static int mid_batch(gprn_handle* h, const double* K, double* W, double* X, const int* d_ids, int nmat, const double* dvec,
+                     const double* vv, double* uv, double* gv, double* logdet, int* mstatus, int do_inverse,
+                     cudaStream_t st) {
+    MidArgs a;
+    a.K = K; a.W = W; a.X = X; a.ids = d_ids; a.Np = h->Np; a.dvec = dvec; a.vv = vv; a.uv = uv; a.gv = gv;
+    a.logdet = logdet; a.mstatus = mstatus; a.do_inverse = do_inverse;
+    a.tstate = (int*)h->mid_state.p;
+    a.zp = (double*)h->mid_zp.p;
+    a.ldpart = (double*)h->mid_ld.p;
+    mid_clear_kernel<<<nmat, 64, 0, st>>>(a.tstate, d_ids);
+    LAUNCH_CHECK(h);
+    mid_pipeline_kernel<<<dim3(h->nt, nmat), MID_THREADS, MID_SMEM, st>>>(a);
+    LAUNCH_CHECK(h);
+    mid_finish_kernel<<<dim3(h->nt, nmat), 256, 0, st>>>(a);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // the engine: `nslot` workspace slots, each holding one evaluation in flight
 // ------------------------------------------------------------------------------------------------
@@ -612,6 +648,13 @@ static int setup_engine(gprn_handle* h, int nslot, Engine& E, bool need_factors 
         if (h->q > 1 && ensure_zeroed(h->XK, matbytes)) return 1;
         if (use_two_level(h->Np) && TRTRI_MAXCH(h->Np) > 1 &&
             ensure(h->gpart, (size_t)nslot * M * (TRTRI_MAXCH(h->Np) - 1) * OUTER_KB * Np * sizeof(double))) return 1;
+    }
+    if (use_mid_path(h)) {
+        // per matrix: tile flags, the z partials [column][row tile][64], the log-det partials [row][lane]
+        const size_t nm_ = (size_t)nslot * M;
+        if (ensure(h->mid_state, nm_ * MID_TILES * sizeof(int))) return 1;
+        if (ensure(h->mid_zp, nm_ * (size_t)MID_MAX_NT * MID_MAX_NT * NB * sizeof(double))) return 1;
+        if (ensure(h->mid_ld, nm_ * MID_MAX_NT * 32 * sizeof(double))) return 1;
     }
     const size_t ve = (size_t)nslot * M * Np;
     if (ensure(h->vecs, 7 * ve * sizeof(double))) return 1;
@@ -710,6 +753,8 @@ static int launch_setup(gprn_handle* h, Engine& E, int nf, ChainView cs, cudaStr
     if (use_small_path(h)) {
         double* scr = (double*)(aux_set ? h->scratch2.p : h->scratch.p);
         if (small_batch(h, E.K, E.d_fida, nf * M, nullptr, nullptr, nullptr, nullptr, c.logdetK, c.mstatus, 0, scr, st)) return 1;
+    } else if (use_mid_path(h)) {
+        if (mid_batch(h, E.K, E.W, E.X, E.d_fida, nf * M, nullptr, nullptr, nullptr, nullptr, c.logdetK, c.mstatus, 0, st)) return 1;
     } else {
         form_a_kernel<<<dim3(ntri, nf * M), 256, 0, st>>>(E.W, E.K, nullptr, E.d_fida, Np);
         LAUNCH_CHECK(h);
@@ -736,6 +781,8 @@ static int launch_iteration(gprn_handle* h, Engine& E, int na, cudaStream_t st, 
     LAUNCH_CHECK(h);
     if (small) {
         if (small_batch(h, E.K, E.d_idn, na * q, c.Dv, c.vv, c.uv, c.gv, c.logdetA, c.mstatus, 1, scr, st)) return 1;
+    } else if (use_mid_path(h)) {
+        if (mid_batch(h, E.K, E.W, E.X, E.d_idn, na * q, c.Dv, c.vv, c.uv, c.gv, c.logdetA, c.mstatus, 1, st)) return 1;
     } else {
         form_a_kernel<<<dim3(ntri, na * q), 256, 0, st>>>(E.W, E.K, c.Dv, E.d_idn, Np);
         LAUNCH_CHECK(h);
@@ -761,6 +808,8 @@ static int launch_iteration(gprn_handle* h, Engine& E, int na, cudaStream_t st, 
     LAUNCH_CHECK(h);
     if (small) {
         if (small_batch(h, E.K, E.d_idw, na * q * p, c.Dv, c.vv, c.uv, c.gv, c.logdetA, c.mstatus, 1, scr, st)) return 1;
+    } else if (use_mid_path(h)) {
+        if (mid_batch(h, E.K, E.W, E.X, E.d_idw, na * q * p, c.Dv, c.vv, c.uv, c.gv, c.logdetA, c.mstatus, 1, st)) return 1;
     } else {
         form_a_kernel<<<dim3(ntri, na * q * p), 256, 0, st>>>(E.W, E.K, c.Dv, E.d_idw, Np);
         LAUNCH_CHECK(h);
@@ -966,7 +1015,9 @@ static int elbo_impl(gprn_handle* h, int64_t B, const double* hyper, bool hyper_
     if (max_iter < 0) max_iter = 10000;                       // meanfield.py:615-616
     {
         const int cap0 = max_slots > 0 ? max_slots : h->max_slots;
-        h->small_mode = decide_small_path(h, cap0 > 0 ? std::min<int64_t>(B, cap0) : B);
+        const int64_t in_flight = cap0 > 0 ? std::min<int64_t>(B, cap0) : B;
+        h->mid_mode = decide_mid_path(h, in_flight);
+        h->small_mode = !h->mid_mode && decide_small_path(h, in_flight);
     }
     int nslot = chunk_size(h, B);
     if (nslot < 1) return fail("gprn_elbo_batched: not enough device memory for one evaluation of this size");

@@ -1,0 +1,263 @@
+// mid.cuh -- latency path for FEW small / mid-size matrices (Np <= 512, q == 1): one matrix is factored and inverted
+// by nt CTAs at once, coupled by per-tile flags in global memory (dataflow), instead of by one CTA walking all tiles
+// (small.cuh: the throughput path for thousands of matrices) or by ~20 dependent launches per matrix (factor.cuh).
+// This is the single-evaluation case -- one ELBOcalc inside an optimiser or sampler step (BASELINE configs C1 / C2) --
+// where the GPU holds M = q(p+1) matrices and the evaluation is ONE dependency chain.
+//
+//   mid_pipeline_kernel, grid = (nt, matrices), 128 threads (four warps = the four 16 x 64 row slabs of a tile):
+//     Cholesky, left-looking: CTA r owns tile ROW r.  For k = 0..r it forms
+//         T_rk = A_rk - sum_{k' < k} L_rk' L_kk'^T
+//       (A fragments straight from its own finished tiles in L2, mma_slab_ga; B tile L_kk' of CTA k through shared
+//       memory, after that tile's flag is up), then factors the diagonal tile (k == r, potrf64) or solves against
+//       L_kk (flag of CTA k) in registers (trsm_rows_inreg), stores L_rk and raises its flag.
+//     Inverse, transposed (Y_ij = X_ij^T, see small.cuh): CTA c owns tile COLUMN c,
+//         Y_ic L_ii^T = [i == c] I - sum_{k=c}^{i-1} Y_kc L_ik^T ,   i = c .. nt-1,
+//       whose only inputs from other CTAs are Cholesky tiles (flags) -- the columns of the inverse are independent
+//       chains.  Y goes to the X buffer (L tiles are still being read by the other columns).  g_c (row sums of squares)
+//       is complete inside the CTA; the column sums that make up z = X v are written per (column, row tile).
+//   mid_finish_kernel, grid = (nt, matrices): adds the z partials and the per-row log-det partials in a fixed order
+//     and forms u_c = sum_{i >= c} Y_ic z_i.
+// Dependencies only point to CTAs with a smaller blockIdx.x of the same matrix (Cholesky) or to Cholesky tiles
+// (inverse), and the host only takes this path when all CTAs of a launch are co-resident, so the flag waits cannot
+// deadlock; they are bounded anyway (a protocol error becomes mstatus = 2, not a hung GPU).
+// Same building blocks and the same summation orders as small.cuh: an evaluation gives bit-identical results whether
+// it runs alone (this path) or inside a large batch (small.cuh) -- tests/test_gpu_parity.py::test_c3_full_size_properties.
+#pragma once
+#include "common.cuh"
+#include "small.cuh"
+
+namespace gprn {
+
+#define MID_MAX_NT 8
+#define MID_TILES (MID_MAX_NT * (MID_MAX_NT + 1) / 2)
+#define MID_THREADS 128
+// P (potrf64 / L_kk / L_ii) + Bm (B operand) + col(128) + pivs(64) + rd(64) + gacc(64) + zpart(4 x 64)
+#define MID_SMEM ((2 * NB * LDT + 4 * NB + NB + 4 * NB) * sizeof(double))
+
+struct MidArgs {
+    const double* K;       // [.][Np][Np] assembled covariance matrices (lower tiles)
+    double* W;             // [.][Np][Np] out: Cholesky factor of K + diag(dvec), lower tiles, row-major
+    double* X;             // [.][Np][Np] out: transposed tiles of the inverse factor (tile (i, j) holds X_ij^T)
+    const int* ids;        // matrix ids
+    int Np;
+    const double* dvec;    // [id][Np] diagonal to add, or null
+    const double* vv;      // [id][Np] right-hand side v (needed when do_inverse)
+    double* uv;            // out [id][Np]  u = X^T X v           (mid_finish_kernel)
+    double* gv;            // out [id][Np]  g = colnorm2(X) = diag(A^-1)
+    double* logdet;        // out [id]                            (mid_finish_kernel)
+    int* mstatus;          // out [id], 1: non-positive pivot, 2: flag wait timed out
+    int* tstate;           // [id][MID_TILES] tile flags, zero at launch: 1 = L tile final
+    double* zp;            // [id][MID_MAX_NT (column)][MID_MAX_NT (row tile)][64] column sums of Y_ic weighted by v_c
+    double* ldpart;        // [id][MID_MAX_NT][32] per-row, per-lane log-det partials (summed as small.cuh sums them)
+    int do_inverse;
+};
+
+__device__ __forceinline__ int mid_tile_index(int I, int J) { return I * (I + 1) / 2 + J; }
+
+// All threads of the CTA return once flag[idx] >= want (thread 0 polls).  The tile behind the flag was written by
+// another CTA: readers use L2 loads (ld.global.cg / cp.async.cg).
+__device__ __forceinline__ void mid_wait(const int* flags, int idx, int want, int* timed_out) {
+    if (threadIdx.x == 0) {
+        const volatile int* f = flags + idx;
+        int spins = 0;
+        while (*f < want) {
+            __nanosleep(32);
+            if (++spins > (1 << 22)) { *timed_out = 1; break; }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void mid_publish(int* flags, int idx, int value) {
+    __threadfence();                   // every thread: its tile stores are visible device-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0) {            // ... before the flag is
+        *reinterpret_cast<volatile int*>(flags + idx) = value;
+        __threadfence();
+    }
+}
+
+__global__ void __launch_bounds__(MID_THREADS, 3) mid_pipeline_kernel(MidArgs a) {
+    GPRN_TRACE_SCOPE(TK_SMALL);
+    extern __shared__ double smem[];
+    double* P = smem;
+    double* Bm = smem + NB * LDT;
+    double* col = smem + 2 * NB * LDT;
+    double* pivs = col + 2 * NB;
+    double* rd = pivs + NB;
+    double* gacc = rd + NB;            // [64] g of this CTA's column
+    double* zpart = gacc + NB;         // [4 warps][64]
+    __shared__ int bad, timed_out;
+    const int Np = a.Np, nt = Np / NB;
+    const int tid = threadIdx.x, w4 = tid >> 5, lane = tid & 31;
+    const int r = lane >> 2, c = lane & 3;
+    const int me = blockIdx.x;                         // tile row (Cholesky) / tile column (inverse)
+    const int id = a.ids[blockIdx.y];
+    const double* Km = a.K + (size_t)id * Np * Np;
+    double* Wm = a.W + (size_t)id * Np * Np;
+    double* Xm = a.X + (size_t)id * Np * Np;
+    const double* dv = a.dvec ? a.dvec + (size_t)id * Np : nullptr;
+    int* flags = a.tstate + (size_t)id * MID_TILES;
+    if (tid == 0) { bad = 0; timed_out = 0; }
+    if (tid < NB) gacc[tid] = 0.0;
+    __syncthreads();
+#define MID_TILE(base, I, J) ((base) + (size_t)((I) * NB) * Np + (J) * NB)
+
+    // ================= Cholesky: tile row `me`, columns k = 0 .. me =================
+    for (int k = 0; k <= me; k++) {
+        double acc[2][8][2];
+#pragma unroll
+        for (int x = 0; x < 2; x++)
+#pragma unroll
+            for (int y = 0; y < 8; y++) {
+                const int m = 16 * w4 + 8 * x + r, n = 8 * y + 2 * c;
+                double2 v = *reinterpret_cast<const double2*>(Km + (size_t)(me * NB + m) * Np + k * NB + n);
+                if (dv && k == me) {
+                    if (m == n) v.x += dv[k * NB + m];
+                    if (m == n + 1) v.y += dv[k * NB + m];
+                }
+                acc[x][y][0] = v.x;
+                acc[x][y][1] = v.y;
+            }
+        for (int kp = 0; kp < k; kp++) {
+            if (k < me) mid_wait(flags, mid_tile_index(k, kp), 1, &timed_out);      // L_k,kp of CTA k (k == me: own tile)
+            load_tile<false>(Bm, MID_TILE(Wm, k, kp), Np, tid, MID_THREADS);
+            __syncthreads();
+            mma_slab_ga<true>(acc, MID_TILE(Wm, me, kp), Np, Bm, w4, lane);
+            __syncthreads();
+        }
+        if (k == me) {
+            slab_store(acc, P, LDT, w4, lane);
+            __syncthreads();
+            potrf64_t<4>(P, LDT, P, rd, col, pivs, &bad, tid);
+            if (tid < 32) a.ldpart[((size_t)id * MID_MAX_NT + me) * 32 + tid] = log(pivs[tid]) + log(pivs[tid + 32]);
+            double* dkk = MID_TILE(Wm, me, me);
+            for (int e = tid; e < NB * (NB / 2); e += MID_THREADS) {
+                const int m = e >> 5, c2 = e & 31;
+                *reinterpret_cast<double2*>(dkk + (size_t)m * Np + 2 * c2) = *reinterpret_cast<const double2*>(P + m * LDT + 2 * c2);
+            }
+        } else {
+            mid_wait(flags, mid_tile_index(k, k), 1, &timed_out);
+            load_tile<false>(P, MID_TILE(Wm, k, k), Np, tid, MID_THREADS);
+            __syncthreads();
+            if (tid < NB) rd[tid] = 1.0 / P[tid * LDT + tid];
+            __syncthreads();
+            trsm_rows_inreg(acc, P, rd, lane);
+            slab_store(acc, MID_TILE(Wm, me, k), Np, w4, lane);
+        }
+        mid_publish(flags, mid_tile_index(me, k), 1);
+    }
+    if (tid == 0 && (bad || timed_out)) a.mstatus[id] = timed_out ? 2 : 1;
+    if (!a.do_inverse) return;
+
+    // ================= inverse: tile column `me`, rows i = me .. nt-1 =================
+    const double* vglob = a.vv + (size_t)id * Np;
+    for (int i = me; i < nt; i++) {
+        double acc[2][8][2];
+#pragma unroll
+        for (int x = 0; x < 2; x++)
+#pragma unroll
+            for (int y = 0; y < 8; y++) {
+                const int n = 16 * w4 + 8 * x + r, m = 8 * y + 2 * c;
+                acc[x][y][0] = (i == me && n == m) ? 1.0 : 0.0;
+                acc[x][y][1] = (i == me && n == m + 1) ? 1.0 : 0.0;
+            }
+        for (int k = me; k < i; k++) {
+            mid_wait(flags, mid_tile_index(i, k), 1, &timed_out);                   // L_ik of CTA i
+            load_tile<false>(Bm, MID_TILE(Wm, i, k), Np, tid, MID_THREADS);
+            __syncthreads();
+            mma_slab_ga<true>(acc, MID_TILE(Xm, k, me), Np, Bm, w4, lane);          // - sum Y_k,me L_ik^T  (own tiles)
+            __syncthreads();
+        }
+        mid_wait(flags, mid_tile_index(i, i), 1, &timed_out);
+        load_tile<false>(P, MID_TILE(Wm, i, i), Np, tid, MID_THREADS);              // L_ii
+        __syncthreads();
+        if (tid < NB) rd[tid] = 1.0 / P[tid * LDT + tid];
+        __syncthreads();
+        trsm_rows_inreg(acc, P, rd, lane, i == me ? 2 * w4 : 0);
+        // g_me[n] += sum_m Y[n][m]^2 : the four lanes of a quad hold one row
+        double vn[2];
+#pragma unroll
+        for (int x = 0; x < 2; x++) {
+            double sg = 0.0;
+#pragma unroll
+            for (int y = 0; y < 8; y++) {
+                sg = fma(acc[x][y][0], acc[x][y][0], sg);
+                sg = fma(acc[x][y][1], acc[x][y][1], sg);
+            }
+            sg += __shfl_xor_sync(0xffffffffu, sg, 1);
+            sg += __shfl_xor_sync(0xffffffffu, sg, 2);
+            const int n = 16 * w4 + 8 * x + r;
+            if (c == 0) gacc[n] += sg;                   // single writer per n
+            vn[x] = vglob[me * NB + n];
+        }
+        // column sums of Y_i,me weighted by v_me: this column's share of z_i
+#pragma unroll
+        for (int y = 0; y < 8; y++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                double t = acc[0][y][e] * vn[0];
+                t = fma(acc[1][y][e], vn[1], t);
+                t += __shfl_xor_sync(0xffffffffu, t, 4);
+                t += __shfl_xor_sync(0xffffffffu, t, 8);
+                t += __shfl_xor_sync(0xffffffffu, t, 16);
+                if (r == 0) zpart[w4 * NB + 8 * y + 2 * c + e] = t;
+            }
+        slab_store(acc, MID_TILE(Xm, i, me), Np, w4, lane);
+        __syncthreads();
+        if (tid < NB)
+            a.zp[(((size_t)id * MID_MAX_NT + me) * MID_MAX_NT + i) * NB + tid] =
+                (zpart[tid] + zpart[NB + tid]) + (zpart[2 * NB + tid] + zpart[3 * NB + tid]);
+        __syncthreads();
+    }
+    if (tid < NB) a.gv[(size_t)id * Np + me * NB + tid] = gacc[tid];
+    if (tid == 0 && timed_out) a.mstatus[id] = 2;
+#undef MID_TILE
+}
+
+// z_i = sum_{j <= i} zp[j][i], u_c = sum_{i >= c} Y_ic z_i, logdet = sum_r ldpart[r] -- each in exactly the order in
+// which small.cuh adds the same terms, so that an evaluation gives the same bits on either path.
+// grid = (nt, matrices), block = 256: thread = (row n of the column's tiles, quarter of the row).
+__global__ void __launch_bounds__(256) mid_finish_kernel(MidArgs a) {
+    __shared__ double z[MID_MAX_NT * NB];
+    const int Np = a.Np, nt = Np / NB, tid = threadIdx.x, me = blockIdx.x;
+    const int id = a.ids[blockIdx.y];
+    if (me == 0 && tid < 32) {         // lane-wise over the rows, then the warp butterfly: the order of small.cuh
+        double s = 0.0;
+        for (int r = 0; r < nt; r++) s += a.ldpart[((size_t)id * MID_MAX_NT + r) * 32 + tid];
+        s = warp_sum(s);
+        if (tid == 0) a.logdet[id] = s;
+    }
+    if (!a.do_inverse) return;
+    for (int e = tid; e < (nt - me) * NB; e += 256) {
+        const int i = me + (e >> 6), m = e & 63;
+        double s = 0.0;
+        for (int j0 = 0; j0 <= i; j0 += 2) {           // pairs of column tiles, as small.cuh adds them
+            double t = a.zp[(((size_t)id * MID_MAX_NT + j0) * MID_MAX_NT + i) * NB + m];
+            if (j0 + 1 <= i) t += a.zp[(((size_t)id * MID_MAX_NT + j0 + 1) * MID_MAX_NT + i) * NB + m];
+            s += t;
+        }
+        z[i * NB + m] = s;
+    }
+    __syncthreads();
+    const double* Xm = a.X + (size_t)id * Np * Np;
+    const int n = tid >> 2, qd = tid & 3;
+    double su = 0.0;
+    for (int i = me; i < nt; i++) {
+        const double* yrow = Xm + (size_t)(i * NB + n) * Np + me * NB + qd * 16;
+        const double* zi = z + i * NB + qd * 16;
+        double2 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = __ldcg(reinterpret_cast<const double2*>(yrow + 2 * e));
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            su = fma(v[e].x, zi[2 * e], su);
+            su = fma(v[e].y, zi[2 * e + 1], su);
+        }
+    }
+    su += __shfl_xor_sync(0xffffffffu, su, 1);
+    su += __shfl_xor_sync(0xffffffffu, su, 2);
+    if (qd == 0) a.uv[(size_t)id * Np + me * NB + n] = su;
+}
+
+}  // namespace gprn

@@ -227,6 +227,10 @@ __global__ void __launch_bounds__(256, 2) small_pipeline_kernel(SmallArgs a) {
                     potrf64(Bs, LDT, Bs, rd, col, pivs, &bad);
                     SMALL_PH(5);
                     if (tid < 32) logsum += log(pivs[tid]) + log(pivs[tid + 32]);
+                    // every solve of the column uses 1 / L_kk by IEEE division (the sub-rounds s > 0 and mid.cuh reload
+                    // L_kk and have nothing else), not potrf64's Newton reciprocal
+                    if (tid < NB) rd[tid] = 1.0 / Bs[tid * LDT + tid];
+                    __syncthreads();
                     if (grp == 0) {
                         double* dkk = small_tile(sc, k, k);
                         for (int e = tid4; e < NB * (NB / 2); e += 128) {

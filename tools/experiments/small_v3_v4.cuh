@@ -1,55 +1,12 @@
 // small_v3_v4.cuh -- two designs of the fused small-N kernel that were built, verified bit-identical on the B200 and
 // measured SLOWER than the shipped one (gpyrn_b200/csrc/small.cuh); kept out of the library, for the record only
 // (DESIGN.md "Tried and rejected", profiles/README.md "fused small-N kernel").  They compile when included after
-// small.cuh (they use its SmallArgs / small_tile / slab_* helpers and common.cuh's potrf64_t / mma_slab_ga).
+// small.cuh (they use its SmallArgs / small_tile / slab_* helpers and common.cuh's potrf64_t / mma_slab_ga; they predate the padded scratch layout).
 //   version 3: 128-thread CTAs, four per SM, one operand tile in shared memory         C3: 14.8 k evaluations/s
 //   version 4: product warps and chain warps on different SM sub-partitions             C3: 13.2 k
 //   shipped  : 256-thread CTAs, two per SM                                              C3: 16.3 k
 #pragma once
 namespace gprn {
-
-// As mma_slab, with the A fragments read STRAIGHT FROM GLOBAL MEMORY (Ag: the 64 x 64 A tile, row-major, leading
-// dimension lda; it sits in the L2-resident scratch): a lane's fragment element A[row][4 ks + c] is an 8-byte load, a
-// quad reads one 32-byte sector, and every element is used by exactly one lane -- staging the A tile in shared memory
-// would only add a copy.  The loads run a chunk of four k-steps (64 DMMAs, ~1000 cycles) ahead of their use, which
-// covers the L2 latency.  Only the B tile (read by all four warps) needs shared memory.
-template <bool NEG>
-__device__ __forceinline__ void mma_slab_ga(double (&acc)[2][8][2], const double* __restrict__ Ag, int lda,
-                                            const double* __restrict__ Bs, int w4, int lane) {
-    const int r = lane >> 2, c = lane & 3;
-    const double* ap = Ag + (size_t)(w4 * 16 + r) * lda + c;
-    const double* bp = Bs + r * LDT + c;
-    double an[4][2];
-#pragma unroll
-    for (int u = 0; u < 4; u++)
-#pragma unroll
-        for (int x = 0; x < 2; x++) an[u][x] = __ldcg(ap + (size_t)x * 8 * lda + 4 * u);
-#pragma unroll
-    for (int ch = 0; ch < 4; ch++) {
-        double ac[4][2];
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-#pragma unroll
-            for (int x = 0; x < 2; x++) ac[u][x] = NEG ? -an[u][x] : an[u][x];
-        if (ch < 3) {
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-#pragma unroll
-                for (int x = 0; x < 2; x++) an[u][x] = __ldcg(ap + (size_t)x * 8 * lda + 16 * (ch + 1) + 4 * u);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int k0 = 16 * ch + 4 * u;
-            double b[8];
-#pragma unroll
-            for (int y = 0; y < 8; y++) b[y] = bp[y * 8 * LDT + k0];
-#pragma unroll
-            for (int x = 0; x < 2; x++)
-#pragma unroll
-                for (int y = 0; y < 8; y++) dmma884(acc[x][y], ac[u][x], b[y]);
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Version 3 (GPRN_SMALL_V3=1): the same algorithm with FOUR matrices resident per SM instead of two.
