@@ -581,12 +581,6 @@ static int small_batch(gprn_handle* h, const double* K, const int* d_ids, int nm
     return 0;
 }
 
-// Clears the tile flags of the listed matrices (the set-up of new sets may run beside an iteration: each launch only
-// touches its own matrices).  grid = (nmat), block = 64.
-__global__ void mid_clear_kernel(int* __restrict__ tstate, const int* __restrict__ ids) {
-    if (threadIdx.x < MID_TILES) tstate[(size_t)ids[blockIdx.x] * MID_TILES + threadIdx.x] = 0;
-}
-
 static int mid_batch(gprn_handle* h, const double* K, double* W, double* X, const int* d_ids, int nmat, const double* dvec,
                      const double* vv, double* uv, double* gv, double* logdet, int* mstatus, int do_inverse,
                      cudaStream_t st) {
@@ -596,8 +590,6 @@ static int mid_batch(gprn_handle* h, const double* K, double* W, double* X, cons
     a.tstate = (int*)h->mid_state.p;
     a.zp = (double*)h->mid_zp.p;
     a.ldpart = (double*)h->mid_ld.p;
-    mid_clear_kernel<<<nmat, 64, 0, st>>>(a.tstate, d_ids);
-    LAUNCH_CHECK(h);
     mid_pipeline_kernel<<<dim3(h->nt, nmat), MID_THREADS, MID_SMEM, st>>>(a);
     LAUNCH_CHECK(h);
     mid_finish_kernel<<<dim3(h->nt, nmat), 256, 0, st>>>(a);
@@ -652,7 +644,7 @@ static int setup_engine(gprn_handle* h, int nslot, Engine& E, bool need_factors 
     if (use_mid_path(h)) {
         // per matrix: tile flags, the z partials [column][row tile][64], the log-det partials [row][lane]
         const size_t nm_ = (size_t)nslot * M;
-        if (ensure(h->mid_state, nm_ * MID_TILES * sizeof(int))) return 1;
+        if (ensure_zeroed(h->mid_state, nm_ * MID_TILES * sizeof(int))) return 1;     // flags: zero between launches (mid_finish_kernel)
         if (ensure(h->mid_zp, nm_ * (size_t)MID_MAX_NT * MID_MAX_NT * NB * sizeof(double))) return 1;
         if (ensure(h->mid_ld, nm_ * MID_MAX_NT * 32 * sizeof(double))) return 1;
     }
@@ -1591,6 +1583,19 @@ extern "C" int gprn_trace_begin(unsigned cap) {
     CU(cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(unsigned)));
     CU(cudaDeviceSynchronize());
     return 0;
+}
+extern "C" int gprn_trace_mid_phases(unsigned long long* out128) {    // [set-up | iteration][row][phase]; resets
+#ifdef GPRN_TRACE
+    unsigned long long tmp[2 * MID_MAX_NT * 8];
+    CU(cudaMemcpyFromSymbol(tmp, g_mid_phase, sizeof(tmp)));
+    memcpy(out128, tmp, sizeof(tmp));
+    memset(tmp, 0, sizeof(tmp));
+    CU(cudaMemcpyToSymbol(g_mid_phase, tmp, sizeof(tmp)));
+    return 0;
+#else
+    (void)out128;
+    return fail("library built without -DGPRN_TRACE");
+#endif
 }
 extern "C" int gprn_trace_small_phases(unsigned long long* out12, int reset) {
     CU(cudaDeviceSynchronize());

@@ -31,8 +31,8 @@ namespace gprn {
 #define MID_MAX_NT 8
 #define MID_TILES (MID_MAX_NT * (MID_MAX_NT + 1) / 2)
 #define MID_THREADS 128
-// P (potrf64 / L_kk / L_ii) + Bm (B operand) + col(128) + pivs(64) + rd(64) + gacc(64) + zpart(4 x 64)
-#define MID_SMEM ((2 * NB * LDT + 4 * NB + NB + 4 * NB) * sizeof(double))
+// P (potrf64 / L_kk / L_ii) + Bm (B operand, two buffers) + col(128) + pivs(64) + rd(64) + gacc(64) + zpart(4 x 64)
+#define MID_SMEM ((3 * NB * LDT + 4 * NB + NB + 4 * NB) * sizeof(double))
 
 struct MidArgs {
     const double* K;       // [.][Np][Np] assembled covariance matrices (lower tiles)
@@ -46,13 +46,30 @@ struct MidArgs {
     double* gv;            // out [id][Np]  g = colnorm2(X) = diag(A^-1)
     double* logdet;        // out [id]                            (mid_finish_kernel)
     int* mstatus;          // out [id], 1: non-positive pivot, 2: flag wait timed out
-    int* tstate;           // [id][MID_TILES] tile flags, zero at launch: 1 = L tile final
+    int* tstate;           // [id][MID_TILES] tile flags, zero at launch (reset by mid_finish_kernel): 1 = L tile final
     double* zp;            // [id][MID_MAX_NT (column)][MID_MAX_NT (row tile)][64] column sums of Y_ic weighted by v_c
     double* ldpart;        // [id][MID_MAX_NT][32] per-row, per-lane log-det partials (summed as small.cuh sums them)
     int do_inverse;
 };
 
 __device__ __forceinline__ int mid_tile_index(int I, int J) { return I * (I + 1) / 2 + J; }
+
+#ifdef GPRN_TRACE
+// thread-0 clock64 by phase and CTA row (development aid): 0 other, 1 flag waits, 2 K loads, 3 products, 4 potrf64,
+// 5 solves, 6 stores + publish, 7 inverse reductions
+__device__ unsigned long long g_mid_phase[2][MID_MAX_NT][8];   // [0: set-up launches, 1: iteration launches]
+#define MID_PH(i)                                                          \
+    do {                                                                   \
+        if (threadIdx.x == 0) {                                            \
+            long long t_ = clock64();                                      \
+            ph_acc[ph_cur] += (unsigned long long)(t_ - ph_last);          \
+            ph_last = t_;                                                  \
+            ph_cur = (i);                                                  \
+        }                                                                  \
+    } while (0)
+#else
+#define MID_PH(i)
+#endif
 
 // All threads of the CTA return once flag[idx] >= want (thread 0 polls).  The tile behind the flag was written by
 // another CTA: readers use L2 loads (ld.global.cg / cp.async.cg).
@@ -71,23 +88,48 @@ __device__ __forceinline__ void mid_wait(const int* flags, int idx, int want, in
 __device__ __forceinline__ void mid_publish(int* flags, int idx, int value) {
     __threadfence();                   // every thread: its tile stores are visible device-wide ...
     __syncthreads();
-    if (threadIdx.x == 0) {            // ... before the flag is
-        *reinterpret_cast<volatile int*>(flags + idx) = value;
-        __threadfence();
-    }
+    if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(flags + idx) = value;      // ... before the flag is
 }
 
-__global__ void __launch_bounds__(MID_THREADS, 3) mid_pipeline_kernel(MidArgs a) {
+// acc -= sum_{t = t0}^{t1 - 1} A_t B_t^T.  A_t = a_tile(t): a finished tile of this CTA, fragments straight from L2
+// (mma_slab_ga); B_t = b_tile(t): staged through the two halves of Bm, the copy of step t + 1 in flight during the
+// products of step t.  ready(t) returns, for all threads and behind a CTA barrier, once B_t may be read (the flag of
+// another CTA's tile, or nothing for an own tile); that barrier also retires the last reader of the buffer about to
+// be overwritten and orders this CTA's own earlier tile stores before the loads.
+template <class FA, class FB, class FR>
+__device__ __forceinline__ void mid_products(double (&acc)[2][8][2], int t0, int t1, FA a_tile, FB b_tile, FR ready,
+                                             double* Bm, int Np, int tid, int w4, int lane) {
+    if (t0 >= t1) return;
+    ready(t0);
+    load_tile<false, false>(Bm, b_tile(t0), Np, tid, MID_THREADS);
+    cp_async_commit();
+    for (int t = t0; t < t1; t++) {
+        const int s = t - t0;
+        if (t + 1 < t1) {
+            ready(t + 1);
+            load_tile<false, false>(Bm + ((s + 1) & 1) * NB * LDT, b_tile(t + 1), Np, tid, MID_THREADS);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        mma_slab_ga<true>(acc, a_tile(t), Np, Bm + (s & 1) * NB * LDT, w4, lane);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(MID_THREADS, 2) mid_pipeline_kernel(MidArgs a) {
     GPRN_TRACE_SCOPE(TK_SMALL);
     extern __shared__ double smem[];
     double* P = smem;
-    double* Bm = smem + NB * LDT;
-    double* col = smem + 2 * NB * LDT;
+    double* Bm = smem + NB * LDT;      // two buffers (mid_products)
+    double* col = smem + 3 * NB * LDT;
     double* pivs = col + 2 * NB;
     double* rd = pivs + NB;
     double* gacc = rd + NB;            // [64] g of this CTA's column
     double* zpart = gacc + NB;         // [4 warps][64]
-    __shared__ int bad, timed_out;
+    __shared__ int bad, timed_out, peek;
     const int Np = a.Np, nt = Np / NB;
     const int tid = threadIdx.x, w4 = tid >> 5, lane = tid & 31;
     const int r = lane >> 2, c = lane & 3;
@@ -101,80 +143,139 @@ __global__ void __launch_bounds__(MID_THREADS, 3) mid_pipeline_kernel(MidArgs a)
     if (tid == 0) { bad = 0; timed_out = 0; }
     if (tid < NB) gacc[tid] = 0.0;
     __syncthreads();
+#ifdef GPRN_TRACE
+    unsigned long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long ph_last = clock64();
+    int ph_cur = 0;
+#endif
 #define MID_TILE(base, I, J) ((base) + (size_t)((I) * NB) * Np + (J) * NB)
-
-    // ================= Cholesky: tile row `me`, columns k = 0 .. me =================
-    for (int k = 0; k <= me; k++) {
-        double acc[2][8][2];
+    auto load_k = [&](double (&t)[2][8][2], int J) {   // K_me,J (+ D on the diagonal tile) in accumulator layout
 #pragma unroll
         for (int x = 0; x < 2; x++)
 #pragma unroll
             for (int y = 0; y < 8; y++) {
                 const int m = 16 * w4 + 8 * x + r, n = 8 * y + 2 * c;
-                double2 v = *reinterpret_cast<const double2*>(Km + (size_t)(me * NB + m) * Np + k * NB + n);
-                if (dv && k == me) {
-                    if (m == n) v.x += dv[k * NB + m];
-                    if (m == n + 1) v.y += dv[k * NB + m];
+                double2 v = *reinterpret_cast<const double2*>(Km + (size_t)(me * NB + m) * Np + J * NB + n);
+                if (dv && J == me) {
+                    if (m == n) v.x += dv[J * NB + m];
+                    if (m == n + 1) v.y += dv[J * NB + m];
                 }
-                acc[x][y][0] = v.x;
-                acc[x][y][1] = v.y;
+                t[x][y][0] = v.x;
+                t[x][y][1] = v.y;
             }
-        for (int kp = 0; kp < k; kp++) {
-            if (k < me) mid_wait(flags, mid_tile_index(k, kp), 1, &timed_out);      // L_k,kp of CTA k (k == me: own tile)
-            load_tile<false>(Bm, MID_TILE(Wm, k, kp), Np, tid, MID_THREADS);
-            __syncthreads();
-            mma_slab_ga<true>(acc, MID_TILE(Wm, me, kp), Np, Bm, w4, lane);
-            __syncthreads();
-        }
-        if (k == me) {
-            slab_store(acc, P, LDT, w4, lane);
-            __syncthreads();
-            potrf64_t<4>(P, LDT, P, rd, col, pivs, &bad, tid);
-            if (tid < 32) a.ldpart[((size_t)id * MID_MAX_NT + me) * 32 + tid] = log(pivs[tid]) + log(pivs[tid + 32]);
-            double* dkk = MID_TILE(Wm, me, me);
-            for (int e = tid; e < NB * (NB / 2); e += MID_THREADS) {
-                const int m = e >> 5, c2 = e & 31;
-                *reinterpret_cast<double2*>(dkk + (size_t)m * Np + 2 * c2) = *reinterpret_cast<const double2*>(P + m * LDT + 2 * c2);
-            }
-        } else {
-            mid_wait(flags, mid_tile_index(k, k), 1, &timed_out);
-            load_tile<false>(P, MID_TILE(Wm, k, k), Np, tid, MID_THREADS);
-            __syncthreads();
-            if (tid < NB) rd[tid] = 1.0 / P[tid * LDT + tid];
-            __syncthreads();
-            trsm_rows_inreg(acc, P, rd, lane);
-            slab_store(acc, MID_TILE(Wm, me, k), Np, w4, lane);
-        }
+    };
+    auto prefetch_k = [&](int J) {     // K_me,J to L2: its HBM latency hides behind the current tile's work
+        const double* nx = Km + (size_t)(me * NB + (tid >> 1)) * Np + J * NB + (tid & 1) * 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 16));
+    };
+
+    // ================= Cholesky: tile row `me`, columns k = 0 .. me =================
+    // The diagonal tile's accumulator accd lives beside the current column's: L_me,k is subtracted from it as soon as
+    // it exists (same order k = 0, 1, .. as the left-looking sum), so that after the last solve of the row only ONE
+    // product stands between L_me,me-1 and potrf64 -- the row's critical path -- instead of `me` of them.
+    double accd[2][8][2];
+    MID_PH(2);
+    load_k(accd, me);
+    if (me > 0) prefetch_k(0);
+    for (int k = 0; k < me; k++) {
+        MID_PH(2);
+        double acc[2][8][2];
+        load_k(acc, k);
+        if (k + 1 < me) prefetch_k(k + 1);
+        MID_PH(3);
+        mid_products(acc, 0, k,
+                     [&](int kp) { return MID_TILE(Wm, me, kp); },
+                     [&](int kp) { return MID_TILE(Wm, k, kp); },                                  // L_k,kp of CTA k
+                     [&](int kp) { mid_wait(flags, mid_tile_index(k, kp), 1, &timed_out); },
+                     Bm, Np, tid, w4, lane);
+        MID_PH(1);
+        mid_wait(flags, mid_tile_index(k, k), 1, &timed_out);
+        MID_PH(5);
+        load_tile<false>(P, MID_TILE(Wm, k, k), Np, tid, MID_THREADS);
+        __syncthreads();
+        if (tid < NB) rd[tid] = 1.0 / P[tid * LDT + tid];
+        __syncthreads();
+        trsm_rows_inreg(acc, P, rd, lane);
+        MID_PH(6);
+        slab_store(acc, MID_TILE(Wm, me, k), Np, w4, lane);
+        slab_store(acc, Bm, LDT, w4, lane);            // and kept on chip: both operands of the diagonal update
         mid_publish(flags, mid_tile_index(me, k), 1);
+        MID_PH(3);
+        mma_slab<true>(accd, Bm, Bm, w4, lane);        // the DMMA sequence of mma_slab_ga: same bits
     }
+    {
+        MID_PH(4);
+        __syncthreads();
+        slab_store(accd, P, LDT, w4, lane);
+        __syncthreads();
+        potrf64_t<4>(P, LDT, P, rd, col, pivs, &bad, tid);
+        MID_PH(6);
+        if (tid < 32) a.ldpart[((size_t)id * MID_MAX_NT + me) * 32 + tid] = log(pivs[tid]) + log(pivs[tid + 32]);
+        double* dkk = MID_TILE(Wm, me, me);
+        for (int e = tid; e < NB * (NB / 2); e += MID_THREADS) {
+            const int m = e >> 5, c2 = e & 31;
+            *reinterpret_cast<double2*>(dkk + (size_t)m * Np + 2 * c2) = *reinterpret_cast<const double2*>(P + m * LDT + 2 * c2);
+        }
+        mid_publish(flags, mid_tile_index(me, me), 1);
+    }
+    MID_PH(0);
     if (tid == 0 && (bad || timed_out)) a.mstatus[id] = timed_out ? 2 : 1;
-    if (!a.do_inverse) return;
+    if (!a.do_inverse) {
+#ifdef GPRN_TRACE
+        if (threadIdx.x == 0)
+            for (int i = 0; i < 8; i++) atomicAdd(&g_mid_phase[0][me][i], ph_acc[i]);
+#endif
+        return;
+    }
 
     // ================= inverse: tile column `me`, rows i = me .. nt-1 =================
+    // Row i is  Y_i,me L_ii^T = [i == me] I - sum_{k = me}^{i-1} Y_k,me L_ik^T.  While L_ii is not there yet the CTA
+    // works ahead on row i + 1 in a second accumulator (its terms k < i: all inputs exist), so that once L_ii arrives
+    // one product, one solve and the reductions finish the row.  Every accumulator still receives its terms in
+    // ascending k: the bits do not depend on how far ahead the CTA got.
     const double* vglob = a.vv + (size_t)id * Np;
-    for (int i = me; i < nt; i++) {
-        double acc[2][8][2];
+    double acc[2][8][2], accn[2][8][2];
+    int kn = me;                       // accn holds the terms k < kn of row i + 1
 #pragma unroll
-        for (int x = 0; x < 2; x++)
+    for (int x = 0; x < 2; x++)
 #pragma unroll
-            for (int y = 0; y < 8; y++) {
-                const int n = 16 * w4 + 8 * x + r, m = 8 * y + 2 * c;
-                acc[x][y][0] = (i == me && n == m) ? 1.0 : 0.0;
-                acc[x][y][1] = (i == me && n == m + 1) ? 1.0 : 0.0;
-            }
-        for (int k = me; k < i; k++) {
-            mid_wait(flags, mid_tile_index(i, k), 1, &timed_out);                   // L_ik of CTA i
-            load_tile<false>(Bm, MID_TILE(Wm, i, k), Np, tid, MID_THREADS);
-            __syncthreads();
-            mma_slab_ga<true>(acc, MID_TILE(Xm, k, me), Np, Bm, w4, lane);          // - sum Y_k,me L_ik^T  (own tiles)
-            __syncthreads();
+        for (int y = 0; y < 8; y++) {
+            const int n = 16 * w4 + 8 * x + r, m = 8 * y + 2 * c;
+            acc[x][y][0] = (n == m) ? 1.0 : 0.0;
+            acc[x][y][1] = (n == m + 1) ? 1.0 : 0.0;
+            accn[x][y][0] = accn[x][y][1] = 0.0;
         }
+    for (int i = me; i < nt; i++) {
+        MID_PH(3);
+        int k0 = kn;                   // acc holds the terms k < k0 of row i
+        mid_products(acc, k0, i,
+                     [&](int k) { return MID_TILE(Xm, k, me); },                                   // own tiles
+                     [&](int k) { return MID_TILE(Wm, i, k); },                                    // L_ik of CTA i
+                     [&](int k) { mid_wait(flags, mid_tile_index(i, k), 1, &timed_out); },
+                     Bm, Np, tid, w4, lane);
+        kn = me;
+        if (i + 1 < nt) {
+            if (tid == 0) peek = *reinterpret_cast<const volatile int*>(flags + mid_tile_index(i, i));
+            __syncthreads();
+            if (peek < 1) {            // CTA-uniform
+                mid_products(accn, me, i,
+                             [&](int k) { return MID_TILE(Xm, k, me); },
+                             [&](int k) { return MID_TILE(Wm, i + 1, k); },
+                             [&](int k) { mid_wait(flags, mid_tile_index(i + 1, k), 1, &timed_out); },
+                             Bm, Np, tid, w4, lane);
+                kn = i;
+            }
+        }
+        MID_PH(1);
         mid_wait(flags, mid_tile_index(i, i), 1, &timed_out);
+        MID_PH(5);
         load_tile<false>(P, MID_TILE(Wm, i, i), Np, tid, MID_THREADS);              // L_ii
         __syncthreads();
         if (tid < NB) rd[tid] = 1.0 / P[tid * LDT + tid];
         __syncthreads();
         trsm_rows_inreg(acc, P, rd, lane, i == me ? 2 * w4 : 0);
+        MID_PH(7);
         // g_me[n] += sum_m Y[n][m]^2 : the four lanes of a quad hold one row
         double vn[2];
 #pragma unroll
@@ -203,13 +304,27 @@ __global__ void __launch_bounds__(MID_THREADS, 3) mid_pipeline_kernel(MidArgs a)
                 t += __shfl_xor_sync(0xffffffffu, t, 16);
                 if (r == 0) zpart[w4 * NB + 8 * y + 2 * c + e] = t;
             }
+        MID_PH(6);
         slab_store(acc, MID_TILE(Xm, i, me), Np, w4, lane);
         __syncthreads();
         if (tid < NB)
             a.zp[(((size_t)id * MID_MAX_NT + me) * MID_MAX_NT + i) * NB + tid] =
                 (zpart[tid] + zpart[NB + tid]) + (zpart[2 * NB + tid] + zpart[3 * NB + tid]);
+#pragma unroll
+        for (int x = 0; x < 2; x++)
+#pragma unroll
+            for (int y = 0; y < 8; y++) {
+                acc[x][y][0] = accn[x][y][0];
+                acc[x][y][1] = accn[x][y][1];
+                accn[x][y][0] = accn[x][y][1] = 0.0;
+            }
         __syncthreads();
     }
+    MID_PH(0);
+#ifdef GPRN_TRACE
+    if (threadIdx.x == 0)
+        for (int i = 0; i < 8; i++) atomicAdd(&g_mid_phase[1][me][i], ph_acc[i]);
+#endif
     if (tid < NB) a.gv[(size_t)id * Np + me * NB + tid] = gacc[tid];
     if (tid == 0 && timed_out) a.mstatus[id] = 2;
 #undef MID_TILE
@@ -222,6 +337,8 @@ __global__ void __launch_bounds__(256) mid_finish_kernel(MidArgs a) {
     __shared__ double z[MID_MAX_NT * NB];
     const int Np = a.Np, nt = Np / NB, tid = threadIdx.x, me = blockIdx.x;
     const int id = a.ids[blockIdx.y];
+    // the pipeline launch is over: its tile flags go back to zero for the next one (they are zero when allocated)
+    if (me == 0 && tid >= 64 && tid < 64 + MID_TILES) a.tstate[(size_t)id * MID_TILES + tid - 64] = 0;
     if (me == 0 && tid < 32) {         // lane-wise over the rows, then the warp butterfly: the order of small.cuh
         double s = 0.0;
         for (int r = 0; r < nt; r++) s += a.ldpart[((size_t)id * MID_MAX_NT + r) * 32 + tid];
@@ -243,17 +360,23 @@ __global__ void __launch_bounds__(256) mid_finish_kernel(MidArgs a) {
     const double* Xm = a.X + (size_t)id * Np * Np;
     const int n = tid >> 2, qd = tid & 3;
     double su = 0.0;
-    for (int i = me; i < nt; i++) {
-        const double* yrow = Xm + (size_t)(i * NB + n) * Np + me * NB + qd * 16;
-        const double* zi = z + i * NB + qd * 16;
-        double2 v[8];
+    double2 v[8], w[8];                // the next tile's row segment is in flight during this one's FMA chain
+    const double* ybase = Xm + (size_t)n * Np + me * NB + qd * 16;
 #pragma unroll
-        for (int e = 0; e < 8; e++) v[e] = __ldcg(reinterpret_cast<const double2*>(yrow + 2 * e));
+    for (int e = 0; e < 8; e++) v[e] = __ldcg(reinterpret_cast<const double2*>(ybase + (size_t)(me * NB) * Np + 2 * e));
+    for (int i = me; i < nt; i++) {
+        if (i + 1 < nt) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) w[e] = __ldcg(reinterpret_cast<const double2*>(ybase + (size_t)((i + 1) * NB) * Np + 2 * e));
+        }
+        const double* zi = z + i * NB + qd * 16;
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             su = fma(v[e].x, zi[2 * e], su);
             su = fma(v[e].y, zi[2 * e + 1], su);
         }
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = w[e];
     }
     su += __shfl_xor_sync(0xffffffffu, su, 1);
     su += __shfl_xor_sync(0xffffffffu, su, 2);
