@@ -4,15 +4,18 @@ Same public surface as the reference's ``gpyrn.covfunc`` for the kernels on the 
 (``SquaredExponential``, ``Periodic``, ``QuasiPeriodic``, ``RationalQuadratic``, ``Matern32``,
 ``Matern52``, ``WhiteNoise`` and their ``+`` / ``*`` compositions; reference gpyrn/covfunc.py:5-80,
 128-288, 355-396), plus the "next" kernels of SURVEY.md 8(f).3 (``Constant``, ``RQP``, ``Cosine``,
-``Exponential``; covfunc.py:107-125, 291-352; ``Derivative`` of SE / Periodic / QuasiPeriodic, covfunc.py:80-104): ``.pars`` float64 array, ``_param_names``, ``_tag``, ``get_parameters`` /
-``set_parameters``, ``k(r)`` on an array of lags.
+``Exponential``; covfunc.py:107-125, 291-352; ``Derivative`` of SE / Periodic / QuasiPeriodic, covfunc.py:80-104) and
+the stationary kernels of the reference's "other" group that work there (``GammaExp``, ``Piecewise``, ``Paciorek``,
+``NewPeriodic``, ``QuasiNewPeriodic``, ``CosPeriodic``, ``QuasiCosPeriodic``; covfunc.py:415-432, 458-546, 645-688):
+``.pars`` float64 array, ``_param_names``, ``_tag``, ``get_parameters`` / ``set_parameters``, ``k(r)`` on an array of
+lags.
 
 The objects hold parameters and structure only.  All arithmetic happens on the GPU: ``k(r)`` ships
 ``r`` through the C ABI (``gprn_keval``), and the inference engine serialises the kernel into a
-postfix program (``program()``) that the assembly kernels interpret.  The other kernels of the
-reference (Linear, GammaExp, Polynomial, Piecewise, Paciorek, the *Periodic variants ... -- SURVEY.md section 2
-row 2) are outside
-the hot-path scope of this package.
+postfix program (``program()``) that the assembly kernels interpret.  The remaining kernels of the
+reference -- ``Linear``, ``Polynomial``, ``HarmonicPeriodic``, ``QuasiHarmonicPeriodic`` (functions of ``(t1, t2)``
+that the reference's own ``inference`` cannot call) and ``NewRQP`` (raises in the reference: ``np.sine``) -- exist as
+names that raise ``NotImplementedError``.
 """
 import numpy as np
 
@@ -22,6 +25,7 @@ from . import _lib
 OP_SE, OP_PER, OP_QP, OP_RQ, OP_M32, OP_M52, OP_WN, OP_ADD, OP_MUL = 1, 2, 3, 4, 5, 6, 7, 100, 101
 OP_CONST, OP_RQP, OP_COS, OP_EXP = 8, 9, 10, 11
 OP_DSE, OP_DPER, OP_DQP = 12, 13, 14
+OP_GEXP, OP_PIECE, OP_PAC, OP_NPER, OP_QNPER, OP_COSP, OP_QCOSP = 15, 16, 17, 18, 19, 20, 21
 
 
 default_device = -1     # GPU used by k(r) on the host-side kernel objects; -1: the thread's current device
@@ -266,22 +270,98 @@ class Matern52(covFunction):
         super().__init__(theta, ell)
 
 
+class GammaExp(covFunction):
+    r""":math:`\theta^2 \exp[-(|r|/\ell)^\gamma]`, :math:`0 < \gamma \le 2` (reference covfunc.py:415-432)"""
+    _param_names = 'theta', 'gamma', 'ell'
+    _tag = 'GammaExp'
+    _opcode = OP_GEXP
+
+    def __init__(self, theta: float, gamma: float, l: float):
+        super().__init__(theta, gamma, l)
+
+
+class Piecewise(covFunction):
+    r"""Third-order piecewise polynomial with compact support: with :math:`x = |r| / (\eta/2)`,
+    :math:`(3x + 1)(1 - x)^3` for :math:`x \le 1`, else 0 (reference covfunc.py:458-474)"""
+    _param_names = 'eta',
+    _tag = 'PW'
+    _opcode = OP_PIECE
+
+    def __init__(self, eta: float):
+        super().__init__(eta)
+
+
+class Paciorek(covFunction):
+    r"""Stationary version of Paciorek's kernel:
+    :math:`a^2 \sqrt{2\ell_1\ell_2/(\ell_1^2+\ell_2^2)}\,\exp[-2r^2/(\ell_1^2+\ell_2^2)]` (reference covfunc.py:477-496).
+    The reference evaluates from the constructor arguments and ignores later ``set_parameters``; here the kernel follows
+    ``pars`` like every other one."""
+    _param_names = 'amplitude', 'ell_1', 'ell_2'
+    _tag = 'PAC'
+    _opcode = OP_PAC
+
+    def __init__(self, amplitude: float, ell_1: float, ell_2: float):
+        super().__init__(amplitude, ell_1, ell_2)
+
+
+class NewPeriodic(covFunction):
+    r"""Rational quadratic mapped to :math:`u(x) = (\cos x, \sin x)`:
+    :math:`a^2 [1 + 2\sin^2(\pi|r|/P)/(\alpha\ell^2)]^{-\alpha}` (reference covfunc.py:499-519)"""
+    _param_names = 'amplitude', 'alpha2', 'P', 'ell'
+    _tag = 'NP'
+    _opcode = OP_NPER
+
+    def __init__(self, amplitude: float, alpha2: float, P: float, l: float):
+        super().__init__(amplitude, alpha2, P, l)
+
+
+class QuasiNewPeriodic(covFunction):
+    r"""``NewPeriodic`` times a squared exponential (reference covfunc.py:522-546)"""
+    _param_names = 'amplitude', 'alpha2', 'ell_e', 'P', 'ell_p'
+    _tag = 'QNP'
+    _opcode = OP_QNPER
+
+    def __init__(self, amplitude: float, alpha2: float, ell_e: float, P: float, ell_p: float):
+        super().__init__(amplitude, alpha2, ell_e, P, ell_p)
+
+
+class CosPeriodic(covFunction):
+    r""":math:`a^2 \exp[-2\cos^2(\pi|r|/P)/\ell^2]` (reference covfunc.py:645-665).  The reference registers only
+    ``(P, ell)`` as ``pars`` (the amplitude is not a parameter there); here all three constructor arguments are."""
+    _param_names = 'amplitude', 'P', 'ell'
+    _tag = 'CP'
+    _opcode = OP_COSP
+
+    def __init__(self, amplitude: float, P: float, ell: float):
+        super().__init__(amplitude, P, ell)
+
+
+class QuasiCosPeriodic(covFunction):
+    r""":math:`a^2 \exp[-2\cos^2(\pi|r|/P)/\ell_p^2 - r^2/(2\ell_e^2)]` (reference covfunc.py:668-688)"""
+    _param_names = 'amplitude', 'ell_e', 'P', 'ell_p'
+    _tag = 'QCP'
+    _opcode = OP_QCOSP
+
+    def __init__(self, amplitude: float, ell_e: float, P: float, ell_p: float):
+        super().__init__(amplitude, ell_e, P, ell_p)
+
+
 # ---------------------------------------------------------------------------------------------
-# Kernels of the reference that are outside the hot-path scope (Linear, GammaExp,
-# Polynomial, Piecewise, Paciorek, the *Periodic variants; several of them are broken in the reference itself).
-# They exist as names so that user code fails with a clear message instead of an AttributeError.
+# Kernels of the reference that cannot run on its own inference path either: Linear, Polynomial and the Harmonic
+# kernels are functions of (t1, t2) while inference calls kernel(r); NewRQP raises (np.sine).  They exist as names so
+# that user code fails with a clear message instead of an AttributeError.
 # ---------------------------------------------------------------------------------------------
 def _out_of_scope(name, ref_line):
     def __init__(self, *args):
         raise NotImplementedError(
             f"covfunc.{name} (reference gpyrn/covfunc.py:{ref_line}) has no device program in gpyrn_b200: the "
             "B200 path covers SquaredExponential, Periodic, QuasiPeriodic, RationalQuadratic, Matern32, Matern52, "
-            "WhiteNoise, Constant, RQP, Cosine, Exponential, Derivative(SE/Periodic/QuasiPeriodic), Sum and "
-            "Multiplication.  There is no CPU fallback.")
+            "WhiteNoise, Constant, RQP, Cosine, Exponential, Derivative(SE/Periodic/QuasiPeriodic), GammaExp, Piecewise, "
+            "Paciorek, NewPeriodic, QuasiNewPeriodic, CosPeriodic, QuasiCosPeriodic, Sum and Multiplication.  "
+            "There is no CPU fallback.")
     return type(name, (covFunction,), {"__init__": __init__, "__doc__": f"Not available on the B200 path ({name})."})
 
 
-for _name, _line in (("Linear", 399), ("GammaExp", 415), ("Polynomial", 435), ("Piecewise", 458), ("Paciorek", 477),
-                     ("NewPeriodic", 499), ("QuasiNewPeriodic", 522), ("NewRQP", 549), ("HarmonicPeriodic", 579),
-                     ("QuasiHarmonicPeriodic", 610), ("CosPeriodic", 645), ("QuasiCosPeriodic", 668)):
+for _name, _line in (("Linear", 399), ("Polynomial", 435), ("NewRQP", 549), ("HarmonicPeriodic", 579),
+                     ("QuasiHarmonicPeriodic", 610)):
     globals()[_name] = _out_of_scope(_name, _line)

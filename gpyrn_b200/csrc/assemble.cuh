@@ -121,6 +121,52 @@ __device__ __forceinline__ double eval_prog(const int32_t* __restrict__ tok, int
                 st[sp++] = (term1 * term2) * term3;
                 pp += 4;
             } break;
+            case GPRN_OP_GEXP: {  // covfunc.py:431-432
+                double th = par[pp], ga = par[pp + 1], l = par[pp + 2];
+                st[sp++] = (th * th) * exp(-pow(ar / l, ga));
+                pp += 3;
+            } break;
+            case GPRN_OP_PIECE: {  // covfunc.py:470-474 (compact support: 0 beyond |r| = eta / 2)
+                double eta = par[pp];
+                double x = fabs(r / (0.5 * eta));
+                double om = 1.0 - x;
+                st[sp++] = x > 1.0 ? 0.0 : (3.0 * x + 1.0) * ((om * om) * om);
+                pp += 1;
+            } break;
+            case GPRN_OP_PAC: {  // covfunc.py:493-496
+                double am = par[pp], l1 = par[pp + 1], l2 = par[pp + 2];
+                double den = l1 * l1 + l2 * l2;
+                double a = sqrt(((2.0 * l1) * l2) / den);
+                double b = exp((((-2.0) * r) * r) / den);
+                st[sp++] = ((am * am) * a) * b;
+                pp += 3;
+            } break;
+            case GPRN_OP_NPER: {  // covfunc.py:517-519
+                double am = par[pp], al = par[pp + 1], P = par[pp + 2], l = par[pp + 3];
+                double s = sin((M_PI * ar) / P);
+                st[sp++] = (am * am) * pow(1.0 + (2.0 * (s * s)) / (al * (l * l)), -al);
+                pp += 4;
+            } break;
+            case GPRN_OP_QNPER: {  // covfunc.py:543-546
+                double am = par[pp], al = par[pp + 1], le = par[pp + 2], P = par[pp + 3], lp = par[pp + 4];
+                double s = sin((M_PI * ar) / P);
+                double a = pow(1.0 + (2.0 * (s * s)) / (al * (lp * lp)), -al);
+                double b = exp(((-0.5) * (r * r)) / (le * le));
+                st[sp++] = ((am * am) * a) * b;
+                pp += 5;
+            } break;
+            case GPRN_OP_COSP: {  // covfunc.py:664-665
+                double am = par[pp], P = par[pp + 1], l = par[pp + 2];
+                double cs = cos((M_PI * ar) / P);
+                st[sp++] = (am * am) * exp(((-2.0) * (cs * cs)) / (l * l));
+                pp += 3;
+            } break;
+            case GPRN_OP_QCOSP: {  // covfunc.py:686-688
+                double am = par[pp], le = par[pp + 1], P = par[pp + 2], lp = par[pp + 3];
+                double cs = cos((M_PI * ar) / P);
+                st[sp++] = (am * am) * exp(((-2.0) * (cs * cs)) / (lp * lp) - (r * r) / (2.0 * (le * le)));
+                pp += 4;
+            } break;
             case GPRN_OP_ADD: {
                 sp--;
                 st[sp - 1] = st[sp - 1] + st[sp];

@@ -138,8 +138,8 @@ __global__ void retire_kernel(ElboCtx c, const int* __restrict__ slots, double* 
     }
 }
 
-// Node right-hand sides (meanfield.py:765, 788-791).  grid = (q, nactive), block = 256.
-__global__ void prep_nodes_kernel(ElboCtx c, const int* __restrict__ sets) {
+// Node right-hand sides (meanfield.py:765, 788-791).  grid = (q, nactive), block = vec_threads.
+__global__ void __launch_bounds__(1024) prep_nodes_kernel(ElboCtx c, const int* __restrict__ sets) {
     GPRN_TRACE_SCOPE(TK_OTHER);
     const int set = sets[blockIdx.y], j = blockIdx.x;
     const int N = c.N, q = c.q, p = c.p;
@@ -170,8 +170,8 @@ __global__ void prep_nodes_kernel(ElboCtx c, const int* __restrict__ sets) {
     }
 }
 
-// Weight right-hand sides (meanfield.py:838, 847-850, 864).  grid = (q*p, nactive), block = 256.
-__global__ void prep_weights_kernel(ElboCtx c, const int* __restrict__ sets) {
+// Weight right-hand sides (meanfield.py:838, 847-850, 864).  grid = (q*p, nactive), block = vec_threads.
+__global__ void __launch_bounds__(1024) prep_weights_kernel(ElboCtx c, const int* __restrict__ sets) {
     GPRN_TRACE_SCOPE(TK_OTHER);
     const int set = sets[blockIdx.y], ji = blockIdx.x, j = ji / c.p, i = ji % c.p;
     const int N = c.N, q = c.q;
@@ -201,9 +201,9 @@ __global__ void prep_weights_kernel(ElboCtx c, const int* __restrict__ sets) {
 // After chol(A), X = L^-1, z = X v, u = X^T z, g = colnorm2(X):  mu = v - D u, diag Sigma = D - D^2 g,
 // entropy and log-prior pieces of this matrix.  use_identity: quadratic form mu^T K^-1 mu = mu.(b - mu/D)
 // (valid when the vector paired with K is the matrix' own mean, i.e. q == 1); otherwise the quadratic
-// forms are added by quad_kernel.  grid = (nmat_per_set, nactive), block = 256; first = first matrix index
+// forms are added by quad_kernel.  grid = (nmat_per_set, nactive), block = vec_threads; first = first matrix index
 // of the phase (0 for nodes, q for weights).
-__global__ void post_kernel(ElboCtx c, const int* __restrict__ sets, int first, int use_identity) {
+__global__ void __launch_bounds__(1024) post_kernel(ElboCtx c, const int* __restrict__ sets, int first, int use_identity) {
     GPRN_TRACE_SCOPE(TK_OTHER);
     __shared__ double red[33];
     const int set = sets[blockIdx.y], m = first + blockIdx.x;
@@ -331,8 +331,11 @@ __global__ void __launch_bounds__(128) cross_frob_kernel(ElboCtx c, const double
     if (tid == 0) c.crossbuf[((size_t)set * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = 0.5 * s;
 }
 
-// Likelihood term, ELBO assembly, stopping rule, state commit.  grid = (nactive), block = 256.
-__global__ void elbo_finish_kernel(ElboCtx c, const int* __restrict__ sets) {
+// Likelihood term, ELBO assembly, stopping rule, state commit; loop_cond != 0: the condition of the WHILE node this
+// kernel runs in.  grid = (nactive), block = 1024 (fixed: the block sums
+// depend on it).
+__global__ void __launch_bounds__(1024) elbo_finish_kernel(ElboCtx c, const int* __restrict__ sets,
+                                                           cudaGraphConditionalHandle loop_cond) {
     GPRN_TRACE_SCOPE(TK_OTHER);
     __shared__ double red[33];
     const int set = sets[blockIdx.x];
@@ -382,6 +385,7 @@ __global__ void elbo_finish_kernel(ElboCtx c, const int* __restrict__ sets) {
         const double MN = (double)c.M * (double)N;
         double ll = -0.5 * s_log - 0.5 * s_res - 0.5 * s_val;
         double lp = 0.0, ent = 0.0;
+#pragma unroll 4
         for (int m = 0; m < c.M; m++) {
             const size_t id = (size_t)set * c.M + m;
             ent += c.ment[id];
@@ -412,7 +416,11 @@ __global__ void elbo_finish_kernel(ElboCtx c, const int* __restrict__ sets) {
             }
             if (!done && it >= c.max_iter) { done = 1; c.status[set] = 2; }
         }
-        if (done) c.active[set] = 0;
+        if (done) {
+            c.active[set] = 0;
+            // device-resident loop (iteration_loop_graph): the first finished set hands control back to the host
+            if (loop_cond) cudaGraphSetConditional(loop_cond, 0);
+        }
     }
 }
 

@@ -142,6 +142,9 @@ struct gprn_handle {
     // CUDA graphs of one lock-step iteration, keyed by the number of active slots (see run_pool)
     std::map<int, cudaGraphExec_t> iter_graphs;
     std::map<int, int64_t> graph_kernels;       // kernel + memset nodes per cached graph (launch accounting)
+    std::map<int, cudaGraphExec_t> loop_graphs; // device-resident iteration loop (WHILE node) per active count
+    std::map<int, int64_t> loop_kernels;        // nodes of the loop body
+    bool loop_unavailable = false;              // the runtime refused the conditional node: per-iteration graphs instead
     std::vector<unsigned char> graph_sig;       // bytes of the Engine (workspace addresses + context) they were captured for
 };
 
@@ -160,6 +163,9 @@ static bool decide_small_path(const gprn_handle* h, int64_t sets_in_flight) {
 // Latency path (mid.cuh): q == 1, N <= 512 and so few matrices in flight that every CTA of a launch (nt per matrix)
 // is resident at once -- a single ELBOcalc, a handful of walkers.  One matrix is then worked on by nt CTAs coupled by
 // tile flags instead of by one CTA (small.cuh) or ~20 dependent launches (factor.cuh).  GPRN_NO_MID=1 disables it.
+// Threads of the O(N) per-matrix kernels (prep_*, post): one element per thread up to 1024.  A function of N only, never
+// of the batch -- post_kernel's block sums depend on it.
+static int vec_threads(const gprn_handle* h) { return std::min(1024, std::max(256, h->Np)); }
 static bool use_mid_path(const gprn_handle* h) { return h->mid_mode; }
 static bool decide_mid_path(const gprn_handle* h, int64_t sets_in_flight) {
     if (h->q != 1 || h->nt > MID_MAX_NT || getenv("GPRN_NO_MID") != nullptr) return false;
@@ -168,8 +174,11 @@ static bool decide_mid_path(const gprn_handle* h, int64_t sets_in_flight) {
 
 static void drop_graphs(gprn_handle* h) {
     for (auto& kv : h->iter_graphs) cudaGraphExecDestroy(kv.second);
+    for (auto& kv : h->loop_graphs) cudaGraphExecDestroy(kv.second);
     h->iter_graphs.clear();
     h->graph_kernels.clear();
+    h->loop_graphs.clear();
+    h->loop_kernels.clear();
     h->graph_sig.clear();
 }
 
@@ -227,7 +236,8 @@ static int set_kernel_attrs(int device) {
     CU(cudaFuncSetAttribute(trtri_inblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
     CU(cudaFuncSetAttribute(small_pipeline_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM + 8192));
     CU(cudaFuncSetAttribute(small_pipeline_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM + 8192));
-    CU(cudaFuncSetAttribute(mid_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM));
+    CU(cudaFuncSetAttribute(mid_pipeline_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM));
+    CU(cudaFuncSetAttribute(mid_pipeline_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM));
     CU(cudaFuncSetAttribute(cross_frob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(predict_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(predict_norm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM128_SMEM));
@@ -370,6 +380,13 @@ static int op_npar(int op) {
         case GPRN_OP_DSE: return 2;
         case GPRN_OP_DPER: return 3;
         case GPRN_OP_DQP: return 4;
+        case GPRN_OP_GEXP: return 3;
+        case GPRN_OP_PIECE: return 1;
+        case GPRN_OP_PAC: return 3;
+        case GPRN_OP_NPER: return 4;
+        case GPRN_OP_QNPER: return 5;
+        case GPRN_OP_COSP: return 3;
+        case GPRN_OP_QCOSP: return 4;
         case GPRN_OP_ADD: case GPRN_OP_MUL: return 0;
         default: return -1;
     }
@@ -590,7 +607,11 @@ static int mid_batch(gprn_handle* h, const double* K, double* W, double* X, cons
     a.tstate = (int*)h->mid_state.p;
     a.zp = (double*)h->mid_zp.p;
     a.ldpart = (double*)h->mid_ld.p;
-    mid_pipeline_kernel<<<dim3(h->nt, nmat), MID_THREADS, MID_SMEM, st>>>(a);
+    // one CTA per SM while they all fit (256 threads: potrf64 on eight warps), else two 128-thread CTAs per SM
+    static const int force_nw = getenv("GPRN_MID_WARPS") ? atoi(getenv("GPRN_MID_WARPS")) : 0;
+    const bool wide = force_nw ? force_nw == 8 : h->nt * nmat <= h->num_sms;
+    if (wide) mid_pipeline_kernel<8><<<dim3(h->nt, nmat), 256, MID_SMEM, st>>>(a);
+    else mid_pipeline_kernel<4><<<dim3(h->nt, nmat), 128, MID_SMEM, st>>>(a);
     LAUNCH_CHECK(h);
     mid_finish_kernel<<<dim3(h->nt, nmat), 256, 0, st>>>(a);
     LAUNCH_CHECK(h);
@@ -661,7 +682,7 @@ static int setup_engine(gprn_handle* h, int nslot, Engine& E, bool need_factors 
     if (ensure(h->lists, nl * sizeof(int))) return 1;
     if (ensure(h->rlist, (size_t)nslot * sizeof(int))) return 1;
     if (ensure_pinned(h->h_lists, h->h_lists_n, nl)) return 1;
-    if (ensure_pinned(h->h_active, h->h_active_n, nslot)) return 1;
+    if (ensure_pinned(h->h_active, h->h_active_n, 3 * (size_t)nslot)) return 1;
     if (ensure_pinned(h->h_ret, h->h_ret_n, nslot)) return 1;
 
     E.nslot = nslot;
@@ -762,14 +783,15 @@ static int launch_setup(gprn_handle* h, Engine& E, int nf, ChainView cs, cudaStr
 // One lock-step fixed-point iteration (meanfield.py:634-646, ELBOaux :651-710) of the `na` active slots listed in
 // E.d_sets: node phase, cross-node terms, weight phase, ELBO + stopping rule.  nmat_other: matrices a concurrent
 // set-up has in flight (only steers the panel-step heuristics).
-static int launch_iteration(gprn_handle* h, Engine& E, int na, cudaStream_t st, int nmat_other) {
+static int launch_iteration(gprn_handle* h, Engine& E, int na, cudaStream_t st, int nmat_other,
+                            cudaGraphConditionalHandle loop_cond = 0) {
     ElboCtx& c = E.c;
     const int q = h->q, p = h->p, M = h->M, Np = h->Np, nt = h->nt, ntri = nt * (nt + 1) / 2;
     const bool small = use_small_path(h);
     double* scr = (double*)h->scratch.p;
     CU(cudaMemsetAsync(c.logdetA, 0, sizeof(double) * (size_t)E.nslot * M, st));
     // node phase
-    prep_nodes_kernel<<<dim3(q, na), 256, 0, st>>>(c, E.d_sets);
+    prep_nodes_kernel<<<dim3(q, na), vec_threads(h), 0, st>>>(c, E.d_sets);
     LAUNCH_CHECK(h);
     if (small) {
         if (small_batch(h, E.K, E.d_idn, na * q, c.Dv, c.vv, c.uv, c.gv, c.logdetA, c.mstatus, 1, scr, st)) return 1;
@@ -781,7 +803,7 @@ static int launch_iteration(gprn_handle* h, Engine& E, int na, cudaStream_t st, 
         if (factor_batch_multi(h, E.W, E.d_idn, na * q, c.logdetA, c.mstatus, E.d_ctr, E.X, st, 0, nmat_other)) return 1;
         if (solve_batch(h, E.X, E.d_idn, na * q, c.vv, c.zv, c.uv, c.gv, st)) return 1;
     }
-    post_kernel<<<dim3(q, na), 256, 0, st>>>(c, E.d_sets, 0, q == 1);
+    post_kernel<<<dim3(q, na), vec_threads(h), 0, st>>>(c, E.d_sets, 0, q == 1);
     LAUNCH_CHECK(h);
     if (q > 1) {
         // Cross-node trace terms (quirk Q3): GEMM-class work that only the ELBO needs.  It runs on its own stream
@@ -796,7 +818,7 @@ static int launch_iteration(gprn_handle* h, Engine& E, int na, cudaStream_t st, 
         CU(cudaEventRecord(h->ev_cross_join, h->cross));
     }
     // weight phase
-    prep_weights_kernel<<<dim3(q * p, na), 256, 0, st>>>(c, E.d_sets);
+    prep_weights_kernel<<<dim3(q * p, na), vec_threads(h), 0, st>>>(c, E.d_sets);
     LAUNCH_CHECK(h);
     if (small) {
         if (small_batch(h, E.K, E.d_idw, na * q * p, c.Dv, c.vv, c.uv, c.gv, c.logdetA, c.mstatus, 1, scr, st)) return 1;
@@ -808,7 +830,7 @@ static int launch_iteration(gprn_handle* h, Engine& E, int na, cudaStream_t st, 
         if (factor_batch_multi(h, E.W, E.d_idw, na * q * p, c.logdetA, c.mstatus, E.d_ctr, E.X, st, 0, nmat_other)) return 1;
         if (solve_batch(h, E.X, E.d_idw, na * q * p, c.vv, c.zv, c.uv, c.gv, st)) return 1;
     }
-    post_kernel<<<dim3(q * p, na), 256, 0, st>>>(c, E.d_sets, q, q == 1);
+    post_kernel<<<dim3(q * p, na), vec_threads(h), 0, st>>>(c, E.d_sets, q, q == 1);
     LAUNCH_CHECK(h);
     if (q > 1) {   // quadratic forms with the reference's vector pairing (quirk Q4)
         gather_quad_vec_kernel<<<dim3(M, na), 256, 0, st>>>(c, E.d_sets, 0);
@@ -819,8 +841,72 @@ static int launch_iteration(gprn_handle* h, Engine& E, int na, cudaStream_t st, 
         LAUNCH_CHECK(h);
     }
     if (q > 1) CU(cudaStreamWaitEvent(st, h->ev_cross_join, 0));
-    elbo_finish_kernel<<<na, 256, 0, st>>>(c, E.d_sets);
+    elbo_finish_kernel<<<na, 1024, 0, st>>>(c, E.d_sets, loop_cond);
     LAUNCH_CHECK(h);
+    return 0;
+}
+
+// The iteration LOOP as one CUDA graph (latency path, mid.cuh): a WHILE conditional node whose body is the captured
+// iteration.  elbo_finish_kernel, the last kernel of the body, clears the node's condition as soon as ANY active set
+// has finished (converged, max_iter, not positive definite), so the device runs lock-step iterations back to back
+// with no host round trip until there is something to retire -- for a single evaluation: the whole fixed-point loop
+// of ELBOcalc (meanfield.py:634-646) in one launch.  The host then polls, retires and refills exactly as after a
+// single iteration.  GPRN_NO_LOOP=1 falls back to one graph launch + poll per iteration.
+static bool use_device_loop(const gprn_handle* h) {
+    static const bool off = getenv("GPRN_NO_LOOP") != nullptr || getenv("GPRN_NO_GRAPH") != nullptr;
+    return !off && !g_debug_sync && !g_profile && !h->loop_unavailable && use_mid_path(h);
+}
+static int iteration_loop_graph(gprn_handle* h, Engine& E, int na, cudaStream_t st) {
+    const unsigned char* eb = reinterpret_cast<const unsigned char*>(&E);
+    if (h->graph_sig.size() != sizeof(Engine) || memcmp(h->graph_sig.data(), eb, sizeof(Engine)) != 0) {
+        drop_graphs(h);
+        h->graph_sig.assign(eb, eb + sizeof(Engine));
+    }
+    auto it = h->loop_graphs.find(na);
+    if (it == h->loop_graphs.end()) {
+        cudaGraph_t g = nullptr;
+        CU(cudaGraphCreate(&g, 0));
+        cudaGraphConditionalHandle cond;
+        cudaError_t e = cudaGraphConditionalHandleCreate(&cond, g, 1, cudaGraphCondAssignDefault);   // 1 at every launch
+        cudaGraphNodeParams np = {};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = cond;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        if (e == cudaSuccess) e = cudaGraphAddNode(&node, g, nullptr, 0, &np);
+        cudaGraph_t body = e == cudaSuccess ? np.conditional.phGraph_out[0] : nullptr;
+        if (e == cudaSuccess) e = cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) {                    // not fatal: one graph launch + poll per iteration instead
+            cudaGraphDestroy(g);
+            cudaGetLastError();
+            h->loop_unavailable = true;
+            return 2;
+        }
+        h->capturing = true;
+        const int64_t before = h->launches;
+        int rc = launch_iteration(h, E, na, st, 0, cond);
+        h->capturing = false;
+        cudaGraph_t captured = nullptr;
+        e = cudaStreamEndCapture(st, &captured);
+        h->launches = before;                      // counted per executed round after the poll
+        if (rc) { cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e)); }
+        size_t nn = 0;
+        CU(cudaGraphGetNodes(body, nullptr, &nn));
+        cudaGraphExec_t ge = nullptr;
+        e = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            h->loop_unavailable = true;
+            return 2;
+        }
+        it = h->loop_graphs.emplace(na, ge).first;
+        h->loop_kernels[na] = (int64_t)nn;
+    }
+    CU(cudaGraphLaunch(it->second, st));
+    h->graph_launches++;
     return 0;
 }
 
@@ -900,7 +986,7 @@ static int run_pool(gprn_handle* h, Engine& E, PoolJob& job, cudaStream_t st) {
     c.max_iter = job.max_iter;
     if ((size_t)S * M > 65535) return fail("internal: too many slots for the launch grids");
     CU(cudaMemsetAsync(E.d_ctr, 0, sizeof(int) * (size_t)S * M, st));
-    std::vector<int> slot_set(S, 0), act, fresh, freeslots, next_act, retired;
+    std::vector<int> slot_set(S, 0), slot_iters(S, 0), act, fresh, freeslots, next_act, retired;
     act.reserve(S); fresh.reserve(S); next_act.reserve(S); retired.reserve(S);
     for (int s = S - 1; s >= 0; s--) freeslots.push_back(s);
     bool empty = false, dirty = true;
@@ -914,6 +1000,7 @@ static int run_pool(gprn_handle* h, Engine& E, PoolJob& job, cudaStream_t st) {
             const int s = freeslots.back();
             freeslots.pop_back();
             slot_set[s] = (int)idx;
+            slot_iters[s] = 0;
             fresh.push_back(s);
         }
         const int na = (int)act.size(), nf = (int)fresh.size();
@@ -931,15 +1018,37 @@ static int run_pool(gprn_handle* h, Engine& E, PoolJob& job, cudaStream_t st) {
             if (launch_setup(h, E, nf, job.cs, st, 0, 0)) return 1;
         }
         if (na) {
-            if (nf ? launch_iteration(h, E, na, st, nf * M) : iteration_graph(h, E, na, st)) return 1;
+            bool looped = !nf && use_device_loop(h);
+            if (looped) {
+                const int rc = iteration_loop_graph(h, E, na, st);
+                if (rc == 1) return 1;
+                if (rc == 2) looped = false;
+            }
+            if (!looped && (nf ? launch_iteration(h, E, na, st, nf * M) : iteration_graph(h, E, na, st))) return 1;
             if (nf) CU(cudaStreamWaitEvent(st, h->ev_side_join, 0));
-            h->last_lockstep_rounds++;
-            // convergence poll: the one host round trip of a round
-            CU(cudaMemcpyAsync(h->h_active, c.active, sizeof(int) * S, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
+            // convergence poll: the one host round trip of a round (of a whole run of rounds with the device loop).
+            // iters | status | active are contiguous: one copy brings the iteration counts along.
+            CU(cudaMemcpyAsync(h->h_active, c.iters, sizeof(int) * 3 * S, cudaMemcpyDeviceToHost, st));
+            if (use_mid_path(h)) {
+                // latency path: the evaluation is a few milliseconds and the caller waits for it -- spin on the stream
+                // instead of a blocking wait, whose wake-up after a multi-millisecond sleep costs up to 0.5 ms
+                cudaError_t qe;
+                while ((qe = cudaStreamQuery(st)) == cudaErrorNotReady) {}
+                if (qe != cudaSuccess) return fail(std::string("cudaStreamQuery: ") + cudaGetErrorString(qe));
+            } else {
+                CU(cudaStreamSynchronize(st));
+            }
+            {
+                const int s0 = act[0];
+                const int64_t rounds = looped ? std::max(1, h->h_active[s0] - slot_iters[s0]) : 1;
+                h->last_lockstep_rounds += rounds;
+                if (looped) h->launches += rounds * h->loop_kernels[na];
+                for (int s : act) slot_iters[s] = h->h_active[s];
+            }
+            const int* h_act = h->h_active + 2 * S;
             next_act.clear();
             retired.clear();
-            for (int s : act) (h->h_active[s] ? next_act : retired).push_back(s);
+            for (int s : act) (h_act[s] ? next_act : retired).push_back(s);
             if (!retired.empty()) {
                 const int nr = (int)retired.size();
                 for (int a = 0; a < nr; a++) h->h_ret[a] = retired[a];

@@ -30,7 +30,6 @@ namespace gprn {
 
 #define MID_MAX_NT 8
 #define MID_TILES (MID_MAX_NT * (MID_MAX_NT + 1) / 2)
-#define MID_THREADS 128
 // P (potrf64 / L_kk / L_ii) + Bm (B operand, two buffers) + col(128) + pivs(64) + rd(64) + gacc(64) + zpart(4 x 64)
 #define MID_SMEM ((3 * NB * LDT + 4 * NB + NB + 4 * NB) * sizeof(double))
 
@@ -96,30 +95,36 @@ __device__ __forceinline__ void mid_publish(int* flags, int idx, int value) {
 // products of step t.  ready(t) returns, for all threads and behind a CTA barrier, once B_t may be read (the flag of
 // another CTA's tile, or nothing for an own tile); that barrier also retires the last reader of the buffer about to
 // be overwritten and orders this CTA's own earlier tile stores before the loads.
-template <class FA, class FB, class FR>
+// NTHR threads stage the B tiles; the warps with `compute` set (the four slab owners) multiply.
+template <int NTHR, class FA, class FB, class FR>
 __device__ __forceinline__ void mid_products(double (&acc)[2][8][2], int t0, int t1, FA a_tile, FB b_tile, FR ready,
-                                             double* Bm, int Np, int tid, int w4, int lane) {
+                                             double* Bm, int Np, int tid, int w4, int lane, bool compute) {
     if (t0 >= t1) return;
     ready(t0);
-    load_tile<false, false>(Bm, b_tile(t0), Np, tid, MID_THREADS);
+    load_tile<false, false>(Bm, b_tile(t0), Np, tid, NTHR);
     cp_async_commit();
     for (int t = t0; t < t1; t++) {
         const int s = t - t0;
         if (t + 1 < t1) {
             ready(t + 1);
-            load_tile<false, false>(Bm + ((s + 1) & 1) * NB * LDT, b_tile(t + 1), Np, tid, MID_THREADS);
+            load_tile<false, false>(Bm + ((s + 1) & 1) * NB * LDT, b_tile(t + 1), Np, tid, NTHR);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
         __syncthreads();
-        mma_slab_ga<true>(acc, a_tile(t), Np, Bm + (s & 1) * NB * LDT, w4, lane);
+        if (compute) mma_slab_ga<true>(acc, a_tile(t), Np, Bm + (s & 1) * NB * LDT, w4, lane);
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(MID_THREADS, 2) mid_pipeline_kernel(MidArgs a) {
+// NW = 4: 128 threads, two CTAs per SM (up to 2 x SMs CTAs in flight).  NW = 8: 256 threads, one CTA per SM -- warps
+// 4-7 only stage tiles and join potrf64 (13 k instead of ~20 k cycles per diagonal tile: the link of the dependency
+// chain that every tile row waits for); the tile arithmetic stays with warps 0-3, so the bits are the same.
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) mid_pipeline_kernel(MidArgs a) {
+    constexpr int NTHR = 32 * NW;
     GPRN_TRACE_SCOPE(TK_SMALL);
     extern __shared__ double smem[];
     double* P = smem;
@@ -131,7 +136,8 @@ __global__ void __launch_bounds__(MID_THREADS, 2) mid_pipeline_kernel(MidArgs a)
     double* zpart = gacc + NB;         // [4 warps][64]
     __shared__ int bad, timed_out, peek;
     const int Np = a.Np, nt = Np / NB;
-    const int tid = threadIdx.x, w4 = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, w4 = (tid >> 5) & 3, lane = tid & 31;
+    const bool compute = tid < 128;                    // the four warps that own the 16 x 64 slabs of a tile
     const int r = lane >> 2, c = lane & 3;
     const int me = blockIdx.x;                         // tile row (Cholesky) / tile column (inverse)
     const int id = a.ids[blockIdx.y];
@@ -165,6 +171,7 @@ __global__ void __launch_bounds__(MID_THREADS, 2) mid_pipeline_kernel(MidArgs a)
             }
     };
     auto prefetch_k = [&](int J) {     // K_me,J to L2: its HBM latency hides behind the current tile's work
+        if (tid >= 128) return;
         const double* nx = Km + (size_t)(me * NB + (tid >> 1)) * Np + J * NB + (tid & 1) * 32;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 16));
@@ -176,44 +183,46 @@ __global__ void __launch_bounds__(MID_THREADS, 2) mid_pipeline_kernel(MidArgs a)
     // product stands between L_me,me-1 and potrf64 -- the row's critical path -- instead of `me` of them.
     double accd[2][8][2];
     MID_PH(2);
-    load_k(accd, me);
+    if (compute) load_k(accd, me);
     if (me > 0) prefetch_k(0);
     for (int k = 0; k < me; k++) {
         MID_PH(2);
         double acc[2][8][2];
-        load_k(acc, k);
+        if (compute) load_k(acc, k);
         if (k + 1 < me) prefetch_k(k + 1);
         MID_PH(3);
-        mid_products(acc, 0, k,
+        mid_products<NTHR>(acc, 0, k,
                      [&](int kp) { return MID_TILE(Wm, me, kp); },
                      [&](int kp) { return MID_TILE(Wm, k, kp); },                                  // L_k,kp of CTA k
                      [&](int kp) { mid_wait(flags, mid_tile_index(k, kp), 1, &timed_out); },
-                     Bm, Np, tid, w4, lane);
+                     Bm, Np, tid, w4, lane, compute);
         MID_PH(1);
         mid_wait(flags, mid_tile_index(k, k), 1, &timed_out);
         MID_PH(5);
-        load_tile<false>(P, MID_TILE(Wm, k, k), Np, tid, MID_THREADS);
+        load_tile<false>(P, MID_TILE(Wm, k, k), Np, tid, NTHR);
         __syncthreads();
         if (tid < NB) rd[tid] = 1.0 / P[tid * LDT + tid];
         __syncthreads();
-        trsm_rows_inreg(acc, P, rd, lane);
-        MID_PH(6);
-        slab_store(acc, MID_TILE(Wm, me, k), Np, w4, lane);
-        slab_store(acc, Bm, LDT, w4, lane);            // and kept on chip: both operands of the diagonal update
+        if (compute) {
+            trsm_rows_inreg(acc, P, rd, lane);
+            MID_PH(6);
+            slab_store(acc, MID_TILE(Wm, me, k), Np, w4, lane);
+            slab_store(acc, Bm, LDT, w4, lane);        // and kept on chip: both operands of the diagonal update
+        }
         mid_publish(flags, mid_tile_index(me, k), 1);
         MID_PH(3);
-        mma_slab<true>(accd, Bm, Bm, w4, lane);        // the DMMA sequence of mma_slab_ga: same bits
+        if (compute) mma_slab<true>(accd, Bm, Bm, w4, lane);      // the DMMA sequence of mma_slab_ga: same bits
     }
     {
         MID_PH(4);
         __syncthreads();
-        slab_store(accd, P, LDT, w4, lane);
+        if (compute) slab_store(accd, P, LDT, w4, lane);
         __syncthreads();
-        potrf64_t<4>(P, LDT, P, rd, col, pivs, &bad, tid);
+        potrf64_t<NW>(P, LDT, P, rd, col, pivs, &bad, tid);
         MID_PH(6);
         if (tid < 32) a.ldpart[((size_t)id * MID_MAX_NT + me) * 32 + tid] = log(pivs[tid]) + log(pivs[tid + 32]);
         double* dkk = MID_TILE(Wm, me, me);
-        for (int e = tid; e < NB * (NB / 2); e += MID_THREADS) {
+        for (int e = tid; e < NB * (NB / 2); e += NTHR) {
             const int m = e >> 5, c2 = e & 31;
             *reinterpret_cast<double2*>(dkk + (size_t)m * Np + 2 * c2) = *reinterpret_cast<const double2*>(P + m * LDT + 2 * c2);
         }
@@ -249,63 +258,65 @@ __global__ void __launch_bounds__(MID_THREADS, 2) mid_pipeline_kernel(MidArgs a)
     for (int i = me; i < nt; i++) {
         MID_PH(3);
         int k0 = kn;                   // acc holds the terms k < k0 of row i
-        mid_products(acc, k0, i,
+        mid_products<NTHR>(acc, k0, i,
                      [&](int k) { return MID_TILE(Xm, k, me); },                                   // own tiles
                      [&](int k) { return MID_TILE(Wm, i, k); },                                    // L_ik of CTA i
                      [&](int k) { mid_wait(flags, mid_tile_index(i, k), 1, &timed_out); },
-                     Bm, Np, tid, w4, lane);
+                     Bm, Np, tid, w4, lane, compute);
         kn = me;
         if (i + 1 < nt) {
             if (tid == 0) peek = *reinterpret_cast<const volatile int*>(flags + mid_tile_index(i, i));
             __syncthreads();
             if (peek < 1) {            // CTA-uniform
-                mid_products(accn, me, i,
+                mid_products<NTHR>(accn, me, i,
                              [&](int k) { return MID_TILE(Xm, k, me); },
                              [&](int k) { return MID_TILE(Wm, i + 1, k); },
                              [&](int k) { mid_wait(flags, mid_tile_index(i + 1, k), 1, &timed_out); },
-                             Bm, Np, tid, w4, lane);
+                             Bm, Np, tid, w4, lane, compute);
                 kn = i;
             }
         }
         MID_PH(1);
         mid_wait(flags, mid_tile_index(i, i), 1, &timed_out);
         MID_PH(5);
-        load_tile<false>(P, MID_TILE(Wm, i, i), Np, tid, MID_THREADS);              // L_ii
+        load_tile<false>(P, MID_TILE(Wm, i, i), Np, tid, NTHR);              // L_ii
         __syncthreads();
         if (tid < NB) rd[tid] = 1.0 / P[tid * LDT + tid];
         __syncthreads();
-        trsm_rows_inreg(acc, P, rd, lane, i == me ? 2 * w4 : 0);
-        MID_PH(7);
-        // g_me[n] += sum_m Y[n][m]^2 : the four lanes of a quad hold one row
-        double vn[2];
-#pragma unroll
-        for (int x = 0; x < 2; x++) {
-            double sg = 0.0;
-#pragma unroll
-            for (int y = 0; y < 8; y++) {
-                sg = fma(acc[x][y][0], acc[x][y][0], sg);
-                sg = fma(acc[x][y][1], acc[x][y][1], sg);
+        if (compute) {
+            trsm_rows_inreg(acc, P, rd, lane, i == me ? 2 * w4 : 0);
+            MID_PH(7);
+            // g_me[n] += sum_m Y[n][m]^2 : the four lanes of a quad hold one row
+            double vn[2];
+    #pragma unroll
+            for (int x = 0; x < 2; x++) {
+                double sg = 0.0;
+    #pragma unroll
+                for (int y = 0; y < 8; y++) {
+                    sg = fma(acc[x][y][0], acc[x][y][0], sg);
+                    sg = fma(acc[x][y][1], acc[x][y][1], sg);
+                }
+                sg += __shfl_xor_sync(0xffffffffu, sg, 1);
+                sg += __shfl_xor_sync(0xffffffffu, sg, 2);
+                const int n = 16 * w4 + 8 * x + r;
+                if (c == 0) gacc[n] += sg;                   // single writer per n
+                vn[x] = vglob[me * NB + n];
             }
-            sg += __shfl_xor_sync(0xffffffffu, sg, 1);
-            sg += __shfl_xor_sync(0xffffffffu, sg, 2);
-            const int n = 16 * w4 + 8 * x + r;
-            if (c == 0) gacc[n] += sg;                   // single writer per n
-            vn[x] = vglob[me * NB + n];
+            // column sums of Y_i,me weighted by v_me: this column's share of z_i
+    #pragma unroll
+            for (int y = 0; y < 8; y++)
+    #pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    double t = acc[0][y][e] * vn[0];
+                    t = fma(acc[1][y][e], vn[1], t);
+                    t += __shfl_xor_sync(0xffffffffu, t, 4);
+                    t += __shfl_xor_sync(0xffffffffu, t, 8);
+                    t += __shfl_xor_sync(0xffffffffu, t, 16);
+                    if (r == 0) zpart[w4 * NB + 8 * y + 2 * c + e] = t;
+                }
         }
-        // column sums of Y_i,me weighted by v_me: this column's share of z_i
-#pragma unroll
-        for (int y = 0; y < 8; y++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                double t = acc[0][y][e] * vn[0];
-                t = fma(acc[1][y][e], vn[1], t);
-                t += __shfl_xor_sync(0xffffffffu, t, 4);
-                t += __shfl_xor_sync(0xffffffffu, t, 8);
-                t += __shfl_xor_sync(0xffffffffu, t, 16);
-                if (r == 0) zpart[w4 * NB + 8 * y + 2 * c + e] = t;
-            }
         MID_PH(6);
-        slab_store(acc, MID_TILE(Xm, i, me), Np, w4, lane);
+        if (compute) slab_store(acc, MID_TILE(Xm, i, me), Np, w4, lane);
         __syncthreads();
         if (tid < NB)
             a.zp[(((size_t)id * MID_MAX_NT + me) * MID_MAX_NT + i) * NB + tid] =
@@ -348,11 +359,18 @@ __global__ void __launch_bounds__(256) mid_finish_kernel(MidArgs a) {
     if (!a.do_inverse) return;
     for (int e = tid; e < (nt - me) * NB; e += 256) {
         const int i = me + (e >> 6), m = e & 63;
+        double zj[MID_MAX_NT];                         // all partials in flight at once, then added in order
+#pragma unroll
+        for (int j = 0; j < MID_MAX_NT; j++)
+            zj[j] = j <= i ? __ldcg(a.zp + (((size_t)id * MID_MAX_NT + j) * MID_MAX_NT + i) * NB + m) : 0.0;
         double s = 0.0;
-        for (int j0 = 0; j0 <= i; j0 += 2) {           // pairs of column tiles, as small.cuh adds them
-            double t = a.zp[(((size_t)id * MID_MAX_NT + j0) * MID_MAX_NT + i) * NB + m];
-            if (j0 + 1 <= i) t += a.zp[(((size_t)id * MID_MAX_NT + j0 + 1) * MID_MAX_NT + i) * NB + m];
-            s += t;
+#pragma unroll
+        for (int j0 = 0; j0 < MID_MAX_NT; j0 += 2) {   // pairs of column tiles, as small.cuh adds them
+            if (j0 <= i) {
+                double t = zj[j0];
+                if (j0 + 1 <= i) t += zj[j0 + 1];
+                s += t;
+            }
         }
         z[i * NB + m] = s;
     }

@@ -47,6 +47,17 @@ enum {
     GPRN_OP_DSE = 12,  /* theta, ell                     */
     GPRN_OP_DPER = 13, /* theta, P, ell                  */
     GPRN_OP_DQP = 14,  /* theta, elle, P, ellp           */
+    /* the stationary "other" kernels of the reference that work there: covfunc.py:415-432 (GammaExp), :458-474
+     * (Piecewise), :477-496 (Paciorek), :499-519 (NewPeriodic), :522-546 (QuasiNewPeriodic), :645-665 (CosPeriodic),
+     * :668-688 (QuasiCosPeriodic).  Linear, Polynomial and the Harmonic kernels take (t1, t2) and cannot be called
+     * by the reference's own inference; NewRQP raises there (np.sine). */
+    GPRN_OP_GEXP = 15,   /* theta, gamma, ell              */
+    GPRN_OP_PIECE = 16,  /* eta                            */
+    GPRN_OP_PAC = 17,    /* amplitude, ell_1, ell_2        */
+    GPRN_OP_NPER = 18,   /* amplitude, alpha2, P, ell      */
+    GPRN_OP_QNPER = 19,  /* amplitude, alpha2, ell_e, P, ell_p */
+    GPRN_OP_COSP = 20,   /* amplitude, P, ell              */
+    GPRN_OP_QCOSP = 21,  /* amplitude, ell_e, P, ell_p     */
     GPRN_OP_ADD = 100,
     GPRN_OP_MUL = 101
 };

@@ -37,6 +37,10 @@ _L.gprn_predict.argtypes = [_v, _d, _d, _d, _d, ctypes.c_int, _d, _d, _d, _d, _d
 
 OPC = {"SE": 1, "P": 2, "QP": 3, "RQ": 4, "M32": 5, "M52": 6, "WN": 7, "C": 8, "RQP": 9, "COS": 10, "EXP": 11}
 DOPC = {"SE": 12, "P": 13, "QP": 14}           # Derivative(k) of the twice-differentiable kernels
+# the stationary "other" kernels carry no `_tag` in the reference: by class name (CosPeriodic registers only (P, ell) as
+# pars there and cannot be bound through pars)
+OPC_BY_CLASS = {"GammaExp": 15, "Piecewise": 16, "Paciorek": 17, "NewPeriodic": 18, "QuasiNewPeriodic": 19,
+                "QuasiCosPeriodic": 21}
 
 
 def program(k):
@@ -48,6 +52,8 @@ def program(k):
         return program(k.k1) + program(k.k2) + [101]
     if name == "Derivative":
         return [DOPC[k.k._tag]]
+    if name in OPC_BY_CLASS:
+        return [OPC_BY_CLASS[name]]
     return [OPC[k._tag]]
 
 

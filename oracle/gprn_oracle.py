@@ -21,6 +21,8 @@ Kernel specification used throughout (a tiny expression tree, no reference class
     ("RQ", theta, alpha, ell) | ("M32", theta, ell) | ("M52", theta, ell) | ("WN", w) |
     ("C", c) | ("RQP", theta, alpha, elle, P, ellp) | ("COS", theta, P) | ("EXP", theta, ell) |
     ("dSE", theta, ell) | ("dP", theta, P, ell) | ("dQP", theta, elle, P, ellp)   [Derivative(k)] |
+    ("GammaExp", theta, gamma, ell) | ("PW", eta) | ("PAC", amp, ell_1, ell_2) | ("NP", amp, alpha2, P, ell) |
+    ("QNP", amp, alpha2, ell_e, P, ell_p) | ("CP", amp, P, ell) | ("QCP", amp, ell_e, P, ell_p) |
     ("sum", spec1, spec2) | ("mul", spec1, spec2)
 """
 from __future__ import annotations
@@ -88,6 +90,27 @@ def kernel_eval(spec, r):
             8 * np.pi ** 2 * le ** 4 * np.sin(np.pi * r / P) ** 2 * np.cos(np.pi * r / P) ** 2
         term3 = np.exp(-(lp ** 2 * r ** 2 + 2 * le ** 2 * np.sin(np.pi * r / P) ** 2) / (lp ** 2 * le ** 2))
         return term1 * term2 * term3
+    if tag == "GammaExp":                 # covfunc.py:431-432
+        return a[0] ** 2 * np.exp(-(np.abs(r) / a[2]) ** a[1])
+    if tag == "PW":                       # covfunc.py:470-474
+        x = r / (0.5 * a[0])
+        pw = (3 * np.abs(x) + 1) * (1 - np.abs(x)) ** 3
+        return np.where(np.abs(x) > 1, 0, pw)
+    if tag == "PAC":                      # covfunc.py:493-496
+        aa = np.sqrt(2 * a[1] * a[2] / (a[1] ** 2 + a[2] ** 2))
+        bb = np.exp(-2 * r * r / (a[1] ** 2 + a[2] ** 2))
+        return a[0] ** 2 * aa * bb
+    if tag == "NP":                       # covfunc.py:517-519
+        aa = (1 + 2 * np.sin(np.pi * np.abs(r) / a[2]) ** 2 / (a[1] * a[3] ** 2)) ** (-a[1])
+        return a[0] ** 2 * aa
+    if tag == "QNP":                      # covfunc.py:543-546
+        aa = (1 + 2 * np.sin(np.pi * np.abs(r) / a[3]) ** 2 / (a[1] * a[4] ** 2)) ** (-a[1])
+        bb = np.exp(-0.5 * r ** 2 / a[2] ** 2)
+        return a[0] ** 2 * aa * bb
+    if tag == "CP":                       # covfunc.py:664-665
+        return a[0] ** 2 * np.exp(-2 * np.cos(np.pi * np.abs(r) / a[1]) ** 2 / a[2] ** 2)
+    if tag == "QCP":                      # covfunc.py:686-688
+        return a[0] ** 2 * np.exp(- 2 * np.cos(np.pi * np.abs(r) / a[2]) ** 2 / a[3] ** 2 - r ** 2 / (2 * a[1] ** 2))
     if tag == "WN":                       # covfunc.py:144-148 (quirk Q9: decided by shape, not by r==0)
         if r.ndim == 2 and r.shape[0] == r.shape[1]:
             return a[0] ** 2 * np.eye(r.shape[0])

@@ -56,7 +56,10 @@ from gpyrn import covfunc, meanfunc, meanfield  # noqa: E402  (the reference its
 KCLS = {"SE": covfunc.SquaredExponential, "P": covfunc.Periodic, "QP": covfunc.QuasiPeriodic,
         "RQ": covfunc.RationalQuadratic, "M32": covfunc.Matern32, "M52": covfunc.Matern52,
         "WN": covfunc.WhiteNoise, "C": covfunc.Constant, "RQP": covfunc.RQP, "COS": covfunc.Cosine,
-        "EXP": covfunc.Exponential}
+        "EXP": covfunc.Exponential,
+        # the stationary "other" kernels (no _tag in the reference; the tags are this repo's)
+        "GammaExp": covfunc.GammaExp, "PW": covfunc.Piecewise, "PAC": covfunc.Paciorek, "NP": covfunc.NewPeriodic,
+        "QNP": covfunc.QuasiNewPeriodic, "CP": covfunc.CosPeriodic, "QCP": covfunc.QuasiCosPeriodic}
 
 
 def build_kernel(spec):
@@ -146,6 +149,32 @@ def kernel_vectors():
         out[f"Krect_{i}"] = k(ts[:, None] - t[None, :])
     np.savez_compressed(os.path.join(HERE, "kernels.npz"), **out)
     print("kernels: ok")
+
+
+def extra_kernel_vectors():
+    """k(r) of the stationary "other" kernels of the reference (covfunc.py:415-432, 458-546, 645-688) on the lag grid
+    of kernel_vectors(), and one ELBO / prediction case that runs them through the whole path (without CosPeriodic /
+    QuasiCosPeriodic: exp(-2 cos^2 x / l^2) has negative Fourier coefficients, the matrices are not positive definite)."""
+    rng = np.random.default_rng(7)
+    t = np.sort(rng.uniform(0, 100, 40))
+    ts = np.linspace(-3, 104, 23)
+    specs = [("GammaExp", 1.2, 1.3, 14.0), ("GammaExp", 0.7, 2.0, 9.0), ("PW", 60.0), ("PW", 250.0),
+             ("PAC", 1.1, 12.0, 30.0), ("NP", 0.9, 1.4, 17.0, 0.8), ("QNP", 1.3, 0.7, 40.0, 21.0, 1.1),
+             ("CP", 0.8, 19.0, 1.2), ("QCP", 1.2, 35.0, 23.0, 0.9),
+             ("sum", ("mul", ("GammaExp", 1.0, 1.5, 30.0), ("PW", 300.0)), ("WN", 0.1)),
+             ("mul", ("QNP", 1.0, 2.0, 80.0, 12.0, 0.9), ("PAC", 1.0, 50.0, 70.0))]
+    out = dict(t=t, tstar=ts, specs=np.array([repr(s) for s in specs]))
+    for i, s in enumerate(specs):
+        k = build_kernel(s)
+        out[f"Ksq_{i}"] = k(t[:, None] - t[None, :])
+        out[f"Krect_{i}"] = k(ts[:, None] - t[None, :])
+    np.savez_compressed(os.path.join(HERE, "extra_kernels.npz"), **out)
+    print("extra kernels: ok")
+    t, ys, es = synth_data(64, 2, seed=13)
+    run_case("other_kernels_64_2_1", t, ys, es, [("QNP", 1.0, 1.5, 60.0, 25.0, 0.9)],
+             [("sum", ("mul", ("GammaExp", 1.1, 1.6, 120.0), ("PW", 900.0)), ("WN", 0.03)),
+              ("sum", ("PAC", 0.9, 70.0, 110.0), ("mul", ("SE", 0.4, 90.0), ("NP", 1.0, 2.0, 50.0, 1.5)))],
+             [0.0, 0.1], [0.1, 0.1], tstar=np.linspace(t[0], t[-1], 31))
 
 
 def big_anchors():
@@ -244,6 +273,9 @@ def main():
     if "--big" in sys.argv:
         os.makedirs(os.path.join(HERE, "big"), exist_ok=True)
         big_anchors()
+        return
+    if "--extra-kernels" in sys.argv:
+        extra_kernel_vectors()
         return
     kernel_vectors()
     if "--kernels" in sys.argv:

@@ -14,8 +14,9 @@ from tests._cases import GOLDEN, golden_names, load_golden, oracle_model, relerr
 SMALL = [n for n in golden_names() if not n.startswith(("c2_", "c1_"))]
 
 
-def test_kernel_vectors():
-    z = np.load(GOLDEN + "/kernels.npz")
+@pytest.mark.parametrize("fixture", ["kernels.npz", "extra_kernels.npz"])
+def test_kernel_vectors(fixture):
+    z = np.load(GOLDEN + "/" + fixture)
     t, ts = z["t"], z["tstar"]
     for i, s in enumerate(z["specs"]):
         spec = ast.literal_eval(str(s))

@@ -30,16 +30,21 @@ def _data(N, p, seed):
     return t, args
 
 
-@pytest.mark.parametrize("shape", [(60, 2, 1), (90, 3, 2)])
+@pytest.mark.parametrize("shape", [(60, 2, 1), (90, 3, 2), (64, 2, 1, "other kernels")])
 def test_stub_on_unmodified_reference(shape, capsys):
     from integration import gpyrn_b200_stub as stub
     covfunc, meanfunc, meanfield = _reference()
-    N, p, q = shape
+    N, p, q = shape[:3]
     t, args = _data(N, p, 17)
     g = meanfield.inference(q, t, *args)
-    nodes = [covfunc.QuasiPeriodic(1 + .2 * j, 60 + 5 * j, 25 + j, .7) if j == 0 else covfunc.Matern52(1.2, 35.0)
-             for j in range(q)]
-    weights = [covfunc.SquaredExponential(1 + .1 * k, 80 + k) for k in range(q * p)]
+    if len(shape) > 3:        # the reference's stationary "other" kernels (bound by class name: they carry no _tag)
+        nodes = [covfunc.QuasiNewPeriodic(1.0, 1.5, 60.0, 25.0, 0.9)]
+        weights = [covfunc.GammaExp(1.1, 1.6, 120.0) * covfunc.Piecewise(900.0) + covfunc.WhiteNoise(0.03),
+                   covfunc.Paciorek(0.9, 70.0, 110.0) + covfunc.SquaredExponential(0.4, 90.0) * covfunc.NewPeriodic(1.0, 2.0, 50.0, 1.5)]
+    else:
+        nodes = [covfunc.QuasiPeriodic(1 + .2 * j, 60 + 5 * j, 25 + j, .7) if j == 0 else covfunc.Matern52(1.2, 35.0)
+                 for j in range(q)]
+        weights = [covfunc.SquaredExponential(1 + .1 * k, 80 + k) for k in range(q * p)]
     g.set_components(nodes, weights, [meanfunc.Constant(0.1 * i) for i in range(p)], [0.1] * p)
     tstar = np.linspace(t[0] - 3, t[-1] + 4, 41)
     # the reference's own CPU path

@@ -1,14 +1,14 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q -k "mid or c3_full or batch_matches or smoke or continuous or elbo_matches" > gpurun_out/w_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/w_pytest.log
-for v in new dbuf; do
-  if [ $v = dbuf ]; then export GPRN_B200_LIB=$PWD/gpurun_out_in/libgprn_dbuf.so; else unset GPRN_B200_LIB; fi
+for v in new w4; do
+  if [ $v = w4 ]; then export GPRN_MID_WARPS=4; else unset GPRN_MID_WARPS; fi
   timeout 200 python bench.py --workload c2 --steps 20 --warmup 5 --no-cpu > gpurun_out/w_c2_$v.json 2> gpurun_out/w_c2_$v.err; echo "c2 $v rc=$?"
 done
-unset GPRN_B200_LIB
+unset GPRN_MID_WARPS
 python - <<'PY'
 import json
-for f in ['w_c2_new','w_c2_dbuf']:
+for f in ['w_c2_new','w_c2_w4']:
     try:
         d=json.loads(open(f'gpurun_out/{f}.json').read().strip().splitlines()[-1])
         print(f,'value',round(d['value'],1),'ms/step',round(d['ms_per_step'],3),'e2e',d['e2e']['value'],'launches/step',d['gpu_launches']/d['steps'],'graphs',d['graph_launches'],'checksum',d['run']['elbo_checksum'],'fail',d['run']['not_converged_or_failed'])
