@@ -278,6 +278,8 @@ __global__ void cross_linear_kernel(ElboCtx c, const int* __restrict__ sets) {
 // Cross-node trace, quadratic part: +0.5 * || X_Kj D_k X_Ak^T ||_F^2 for k < j.
 // C[a][b] = sum_{n <= min(a,b)} XK_j[a][n] D_k[n] XA_k[b][n]; one CTA per 64x64 tile of C.
 // grid = (nt*nt, npairs, nactive), block = 128, dynamic shared memory 2*TILE_SMEM.
+// TR: the factors are stored as transposed tiles (latency path, mid.cuh): the operand tiles are transposed on load.
+template <bool TR>
 __global__ void __launch_bounds__(128) cross_frob_kernel(ElboCtx c, const double* __restrict__ XK,
                                                          const double* __restrict__ XA,
                                                          const int* __restrict__ sets) {
@@ -305,8 +307,8 @@ __global__ void __launch_bounds__(128) cross_frob_kernel(ElboCtx c, const double
     const int kmax = min(ta, tb);
     __shared__ double sc[NB];
     for (int kt = 0; kt <= kmax; kt++) {
-        load_tile<false, false>(As, xk + (size_t)(ta * NB) * Np + kt * NB, Np, tid, 128);
-        load_tile<false, false>(Bs, xa + (size_t)(tb * NB) * Np + kt * NB, Np, tid, 128);
+        load_tile<TR, false>(As, xk + (size_t)(ta * NB) * Np + kt * NB, Np, tid, 128);
+        load_tile<TR, false>(Bs, xa + (size_t)(tb * NB) * Np + kt * NB, Np, tid, 128);
         if (tid < NB) sc[tid] = Dk[kt * NB + tid];
         cp_async_commit();
         cp_async_wait<0>();

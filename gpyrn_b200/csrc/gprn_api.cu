@@ -160,15 +160,18 @@ static bool decide_small_path(const gprn_handle* h, int64_t sets_in_flight) {
     return h->nt <= 4 || sets_in_flight * h->M >= 2 * (int64_t)h->num_sms;
 }
 
-// Latency path (mid.cuh): q == 1, N <= 512 and so few matrices in flight that every CTA of a launch (nt per matrix)
-// is resident at once -- a single ELBOcalc, a handful of walkers.  One matrix is then worked on by nt CTAs coupled by
-// tile flags instead of by one CTA (small.cuh) or ~20 dependent launches (factor.cuh).  GPRN_NO_MID=1 disables it.
 // Threads of the O(N) per-matrix kernels (prep_*, post): one element per thread up to 1024.  A function of N only, never
 // of the batch -- post_kernel's block sums depend on it.
 static int vec_threads(const gprn_handle* h) { return std::min(1024, std::max(256, h->Np)); }
+
+// Latency path (mid.cuh): N <= 512 and so few matrices in flight that every CTA of a launch (nt per matrix) is
+// resident at once -- a single ELBOcalc, a handful of walkers.  One matrix is then worked on by nt CTAs coupled by
+// tile flags instead of by one CTA (small.cuh) or ~20 dependent launches (factor.cuh).  Any q: for q > 1 the set-up
+// also inverts chol(K) (transposed tiles, read by cross_frob_kernel<true> and mid_trmv_lower_kernel).
+// GPRN_NO_MID=1 disables it.
 static bool use_mid_path(const gprn_handle* h) { return h->mid_mode; }
 static bool decide_mid_path(const gprn_handle* h, int64_t sets_in_flight) {
-    if (h->q != 1 || h->nt > MID_MAX_NT || getenv("GPRN_NO_MID") != nullptr) return false;
+    if (h->nt > MID_MAX_NT || getenv("GPRN_NO_MID") != nullptr) return false;
     return sets_in_flight * h->M * h->nt <= 2 * (int64_t)h->num_sms;
 }
 
@@ -238,7 +241,8 @@ static int set_kernel_attrs(int device) {
     CU(cudaFuncSetAttribute(small_pipeline_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM + 8192));
     CU(cudaFuncSetAttribute(mid_pipeline_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM));
     CU(cudaFuncSetAttribute(mid_pipeline_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM));
-    CU(cudaFuncSetAttribute(cross_frob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
+    CU(cudaFuncSetAttribute(cross_frob_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
+    CU(cudaFuncSetAttribute(cross_frob_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(predict_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TILE_SMEM)));
     CU(cudaFuncSetAttribute(predict_norm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM128_SMEM));
     g_attr_devices.insert(device);
@@ -767,7 +771,9 @@ static int launch_setup(gprn_handle* h, Engine& E, int nf, ChainView cs, cudaStr
         double* scr = (double*)(aux_set ? h->scratch2.p : h->scratch.p);
         if (small_batch(h, E.K, E.d_fida, nf * M, nullptr, nullptr, nullptr, nullptr, c.logdetK, c.mstatus, 0, scr, st)) return 1;
     } else if (use_mid_path(h)) {
-        if (mid_batch(h, E.K, E.W, E.X, E.d_fida, nf * M, nullptr, nullptr, nullptr, nullptr, c.logdetK, c.mstatus, 0, st)) return 1;
+        // q > 1: the cross-node terms and the prior's quadratic forms need L_K^-1 (transposed tiles) and diag(K^-1)
+        if (mid_batch(h, E.K, E.W, q > 1 ? E.XK : E.X, E.d_fida, nf * M, nullptr, nullptr, nullptr, q > 1 ? c.gK : nullptr,
+                      c.logdetK, c.mstatus, q > 1 ? 1 : 0, st)) return 1;
     } else {
         form_a_kernel<<<dim3(ntri, nf * M), 256, 0, st>>>(E.W, E.K, nullptr, E.d_fida, Np);
         LAUNCH_CHECK(h);
@@ -805,7 +811,14 @@ static int launch_iteration(gprn_handle* h, Engine& E, int na, cudaStream_t st, 
     }
     post_kernel<<<dim3(q, na), vec_threads(h), 0, st>>>(c, E.d_sets, 0, q == 1);
     LAUNCH_CHECK(h);
-    if (q > 1) {
+    if (q > 1 && use_mid_path(h)) {
+        // latency path: small matrices, factors stored as transposed tiles; no extra stream (the whole iteration is
+        // the body of a conditional graph node)
+        cross_linear_kernel<<<na, 256, 0, st>>>(c, E.d_sets);
+        LAUNCH_CHECK(h);
+        cross_frob_kernel<true><<<dim3(nt * nt, q * (q - 1) / 2, na), 128, 2 * TILE_SMEM, st>>>(c, E.XK, E.X, E.d_sets);
+        LAUNCH_CHECK(h);
+    } else if (q > 1) {
         // Cross-node trace terms (quirk Q3): GEMM-class work that only the ELBO needs.  It runs on its own stream
         // beside the latency-bound start of the weight phase (it reads the node matrices' D and X, which the weight
         // phase does not touch) and is joined before elbo_finish_kernel.
@@ -813,7 +826,7 @@ static int launch_iteration(gprn_handle* h, Engine& E, int na, cudaStream_t st, 
         CU(cudaStreamWaitEvent(h->cross, h->ev_cross_fork, 0));
         cross_linear_kernel<<<na, 256, 0, h->cross>>>(c, E.d_sets);
         LAUNCH_CHECK(h);
-        cross_frob_kernel<<<dim3(nt * nt, q * (q - 1) / 2, na), 128, 2 * TILE_SMEM, h->cross>>>(c, E.XK, E.X, E.d_sets);
+        cross_frob_kernel<false><<<dim3(nt * nt, q * (q - 1) / 2, na), 128, 2 * TILE_SMEM, h->cross>>>(c, E.XK, E.X, E.d_sets);
         LAUNCH_CHECK(h);
         CU(cudaEventRecord(h->ev_cross_join, h->cross));
     }
@@ -835,12 +848,13 @@ static int launch_iteration(gprn_handle* h, Engine& E, int na, cudaStream_t st, 
     if (q > 1) {   // quadratic forms with the reference's vector pairing (quirk Q4)
         gather_quad_vec_kernel<<<dim3(M, na), 256, 0, st>>>(c, E.d_sets, 0);
         LAUNCH_CHECK(h);
-        trmv_lower_kernel<<<dim3(Np / 8, na * M), 256, 0, st>>>(c.zv, E.XK, c.vv, E.d_ida, nullptr, Np);
+        if (use_mid_path(h)) mid_trmv_lower_kernel<<<dim3(nt, na * M), 256, 0, st>>>(c.zv, E.XK, c.vv, E.d_ida, Np);
+        else trmv_lower_kernel<<<dim3(Np / 8, na * M), 256, 0, st>>>(c.zv, E.XK, c.vv, E.d_ida, nullptr, Np);
         LAUNCH_CHECK(h);
         quad_kernel<<<dim3(M, na), 256, 0, st>>>(c, E.d_sets, 0);
         LAUNCH_CHECK(h);
     }
-    if (q > 1) CU(cudaStreamWaitEvent(st, h->ev_cross_join, 0));
+    if (q > 1 && !use_mid_path(h)) CU(cudaStreamWaitEvent(st, h->ev_cross_join, 0));
     elbo_finish_kernel<<<na, 1024, 0, st>>>(c, E.d_sets, loop_cond);
     LAUNCH_CHECK(h);
     return 0;

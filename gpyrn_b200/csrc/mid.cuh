@@ -40,7 +40,7 @@ struct MidArgs {
     const int* ids;        // matrix ids
     int Np;
     const double* dvec;    // [id][Np] diagonal to add, or null
-    const double* vv;      // [id][Np] right-hand side v (needed when do_inverse)
+    const double* vv;      // [id][Np] right-hand side v (with do_inverse; null together with uv: no z / u)
     double* uv;            // out [id][Np]  u = X^T X v           (mid_finish_kernel)
     double* gv;            // out [id][Np]  g = colnorm2(X) = diag(A^-1)
     double* logdet;        // out [id]                            (mid_finish_kernel)
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) mid_pipeline_kernel(
     // works ahead on row i + 1 in a second accumulator (its terms k < i: all inputs exist), so that once L_ii arrives
     // one product, one solve and the reductions finish the row.  Every accumulator still receives its terms in
     // ascending k: the bits do not depend on how far ahead the CTA got.
-    const double* vglob = a.vv + (size_t)id * Np;
+    const double* vglob = a.vv ? a.vv + (size_t)id * Np : nullptr;      // null: inverse and g only (set-up, q > 1)
     double acc[2][8][2], accn[2][8][2];
     int kn = me;                       // accn holds the terms k < kn of row i + 1
 #pragma unroll
@@ -288,10 +288,10 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) mid_pipeline_kernel(
             MID_PH(7);
             // g_me[n] += sum_m Y[n][m]^2 : the four lanes of a quad hold one row
             double vn[2];
-    #pragma unroll
+#pragma unroll
             for (int x = 0; x < 2; x++) {
                 double sg = 0.0;
-    #pragma unroll
+#pragma unroll
                 for (int y = 0; y < 8; y++) {
                     sg = fma(acc[x][y][0], acc[x][y][0], sg);
                     sg = fma(acc[x][y][1], acc[x][y][1], sg);
@@ -300,12 +300,12 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) mid_pipeline_kernel(
                 sg += __shfl_xor_sync(0xffffffffu, sg, 2);
                 const int n = 16 * w4 + 8 * x + r;
                 if (c == 0) gacc[n] += sg;                   // single writer per n
-                vn[x] = vglob[me * NB + n];
+                vn[x] = vglob ? vglob[me * NB + n] : 0.0;
             }
             // column sums of Y_i,me weighted by v_me: this column's share of z_i
-    #pragma unroll
+#pragma unroll
             for (int y = 0; y < 8; y++)
-    #pragma unroll
+#pragma unroll
                 for (int e = 0; e < 2; e++) {
                     double t = acc[0][y][e] * vn[0];
                     t = fma(acc[1][y][e], vn[1], t);
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(256) mid_finish_kernel(MidArgs a) {
         s = warp_sum(s);
         if (tid == 0) a.logdet[id] = s;
     }
-    if (!a.do_inverse) return;
+    if (!a.do_inverse || !a.uv) return;
     for (int e = tid; e < (nt - me) * NB; e += 256) {
         const int i = me + (e >> 6), m = e & 63;
         double zj[MID_MAX_NT];                         // all partials in flight at once, then added in order
@@ -399,6 +399,30 @@ __global__ void __launch_bounds__(256) mid_finish_kernel(MidArgs a) {
     su += __shfl_xor_sync(0xffffffffu, su, 1);
     su += __shfl_xor_sync(0xffffffffu, su, 2);
     if (qd == 0) a.uv[(size_t)id * Np + me * NB + n] = su;
+}
+
+// z = X v for an inverse factor stored as TRANSPOSED tiles (tile (I, J) of the buffer holds X_IJ^T, as this path writes
+// it):  z_I[a] = sum_{J <= I} sum_n T_IJ[n][a] v_J[n].  Used for the prior's quadratic forms m^T K^-1 m = ||X_K m||^2
+// when q > 1 (quirk Q4 pairs K with a vector that is not its own mean, so the q = 1 identity does not apply).
+// grid = (nt, matrices), block = 256: thread = (column a of the tile row, quarter of the 64 n of a tile); the four
+// quarters are added in a fixed order.
+__global__ void __launch_bounds__(256) mid_trmv_lower_kernel(double* __restrict__ z, const double* __restrict__ XT,
+                                                             const double* __restrict__ v, const int* __restrict__ ids,
+                                                             int Np) {
+    __shared__ double part[4][NB];
+    const int id = ids[blockIdx.y], I = blockIdx.x, a = threadIdx.x & 63, qd = threadIdx.x >> 6;
+    const double* Xm = XT + (size_t)id * Np * Np;
+    const double* vv = v + (size_t)id * Np;
+    double s = 0.0;
+    for (int J = 0; J <= I; J++) {
+        const double* T = Xm + (size_t)(I * NB + qd * 16) * Np + J * NB + a;      // T[n][a], n = 16 qd ..
+        const double* vj = vv + J * NB + qd * 16;
+#pragma unroll
+        for (int n = 0; n < 16; n++) s = fma(__ldcg(T + (size_t)n * Np), vj[n], s);
+    }
+    part[qd][a] = s;
+    __syncthreads();
+    if (qd == 0) z[(size_t)id * Np + I * NB + a] = (part[0][a] + part[1][a]) + (part[2][a] + part[3][a]);
 }
 
 }  // namespace gprn
