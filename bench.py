@@ -100,6 +100,16 @@ class ClockSampler(threading.Thread):
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.first = 0                 # rows before this index were sampled during the warm-up
+
+    def mark(self):
+        """The timed region starts now: only samples from here on are reported.  (The thread is started before the
+        warm-up so that the start-up of the nvidia-smi process -- NVML initialisation, hundreds of milliseconds that
+        stall driver calls -- does not fall into a timed region that may itself be only tens of milliseconds long.)"""
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < 5.0:       # a warm-up shorter than that start-up
+            time.sleep(0.01)
+        self.first = len(self.rows)
 
     def run(self):
         try:
@@ -113,8 +123,9 @@ class ClockSampler(threading.Thread):
     def stop(self):
         if self.proc:
             self.proc.terminate()
+        rows = self.rows[self.first:] or self.rows[-1:]       # a timed region shorter than the sampling period
         sm, reasons, mx = [], set(), None
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx = float(r[2])
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -343,12 +354,14 @@ def measure(args, w, wname, steps, warmup, e2e_cap, with_cpu, tag=""):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(warmup):
-        step_dev(args.warmup_pool * world if args.warmup_pool else None)
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    for _ in range(warmup):
+        step_dev(args.warmup_pool * world if args.warmup_pool else None)
+    barrier()
+    if sampler:
+        sampler.mark()
     L.gprn_reset_launch_count(h)
     ms = 0.0
     rounds = 0

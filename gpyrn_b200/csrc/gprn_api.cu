@@ -103,6 +103,8 @@ struct gprn_handle {
     bool capturing = false;                     // inside a stream capture (CUDA graph of one iteration)
     bool small_mode = false;                    // this call runs the fused small-N pipeline (decide_small_path)
     bool mid_mode = false;                      // this call runs the multi-CTA dataflow pipeline (decide_mid_path)
+    int* mid_ticket = nullptr;                  // two start-order counters behind the tile flags (mid.cuh)
+    bool mid_latency = false;                   // mid_mode with every CTA resident at once (a few evaluations in flight)
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // stream groups: set 0 for the fixed-point iteration, set 1 for the set-up of newly admitted sets, which runs
@@ -149,15 +151,21 @@ struct gprn_handle {
 };
 
 // Fused single-kernel pipeline (small.cuh): q == 1 (no cross-node terms, which need the factors in HBM) and
-// N <= 256 always; N <= 512 when the call keeps at least two matrices per SM in flight -- one persistent CTA walks a
-// whole matrix, so a handful of mid-size matrices is better served by the multi-CTA kernels of factor.cuh.
+// N <= 256 always; N <= 512 when the call keeps at least eight matrices per SM in flight -- one persistent CTA walks a
+// whole matrix, so fewer mid-size matrices are better served by the dataflow kernels of mid.cuh (nt CTAs per matrix).
 // Decided per call (decide_small_path) because the workspace layout differs.  GPRN_NO_SMALL=1 disables the path,
-// GPRN_SMALL_MAX_NT=4 restricts it to N <= 256.
+// GPRN_SMALL_MAX_NT=4 restricts it to N <= 256, GPRN_SMALL_MIN_FILL sets the matrices per SM it wants above N = 256.
 static bool use_small_path(const gprn_handle* h) { return h->small_mode; }
 static bool decide_small_path(const gprn_handle* h, int64_t sets_in_flight) {
     static const int max_nt = getenv("GPRN_SMALL_MAX_NT") ? atoi(getenv("GPRN_SMALL_MAX_NT")) : SMALL_MAX_NT;
     if (h->q != 1 || h->nt > std::min(max_nt, SMALL_MAX_NT) || getenv("GPRN_NO_SMALL") != nullptr) return false;
-    return h->nt <= 4 || sets_in_flight * h->M >= 2 * (int64_t)h->num_sms;
+    // nt > 4: the dataflow kernels (mid.cuh, throughput mode) keep every SM busy with any number of matrices, the
+    // persistent single-CTA kernel needs several matrices per resident CTA to amortise its tail.  Measured at N = 500,
+    // p = 4 (evaluations/s, fused : dataflow): 128 sets 1.97 k : ~2.5 k, 512 sets 2.88 k : 2.56 k.
+    // GPRN_SMALL_MIN_FILL overrides the matrices-per-SM threshold.
+    const char* fe = getenv("GPRN_SMALL_MIN_FILL");
+    const int fill = fe ? std::max(1, atoi(fe)) : 8;
+    return h->nt <= 4 || sets_in_flight * h->M >= fill * (int64_t)h->num_sms;
 }
 
 // Threads of the O(N) per-matrix kernels (prep_*, post): one element per thread up to 1024.  A function of N only, never
@@ -170,9 +178,17 @@ static int vec_threads(const gprn_handle* h) { return std::min(1024, std::max(25
 // also inverts chol(K) (transposed tiles, read by cross_frob_kernel<true> and mid_trmv_lower_kernel).
 // GPRN_NO_MID=1 disables it.
 static bool use_mid_path(const gprn_handle* h) { return h->mid_mode; }
+static bool mid_colocated(const gprn_handle* h, int64_t sets_in_flight) {
+    return sets_in_flight * h->M * h->nt <= 2 * (int64_t)h->num_sms;
+}
 static bool decide_mid_path(const gprn_handle* h, int64_t sets_in_flight) {
     if (h->nt > MID_MAX_NT || getenv("GPRN_NO_MID") != nullptr) return false;
-    return sets_in_flight * h->M * h->nt <= 2 * (int64_t)h->num_sms;
+    if (mid_colocated(h, sets_in_flight)) return true;                 // latency mode
+    // throughput mode (CTAs numbered by start order): wherever the fused single-CTA kernel does not apply -- q > 1, or
+    // 256 < N <= 512 with too few matrices to give every SM two -- instead of the ~20 dependent launches per matrix
+    // of factor.cuh.  GPRN_MID_COLOCATED_ONLY=1 restores the multi-kernel path there.
+    if (getenv("GPRN_MID_COLOCATED_ONLY") != nullptr) return false;
+    return !decide_small_path(h, sets_in_flight);
 }
 
 static void drop_graphs(gprn_handle* h) {
@@ -604,7 +620,7 @@ static int small_batch(gprn_handle* h, const double* K, const int* d_ids, int nm
 
 static int mid_batch(gprn_handle* h, const double* K, double* W, double* X, const int* d_ids, int nmat, const double* dvec,
                      const double* vv, double* uv, double* gv, double* logdet, int* mstatus, int do_inverse,
-                     cudaStream_t st) {
+                     cudaStream_t st, int aux_set = 0 /* 1: the set-up stream running beside an iteration */) {
     MidArgs a;
     a.K = K; a.W = W; a.X = X; a.ids = d_ids; a.Np = h->Np; a.dvec = dvec; a.vv = vv; a.uv = uv; a.gv = gv;
     a.logdet = logdet; a.mstatus = mstatus; a.do_inverse = do_inverse;
@@ -614,6 +630,8 @@ static int mid_batch(gprn_handle* h, const double* K, double* W, double* X, cons
     // one CTA per SM while they all fit (256 threads: potrf64 on eight warps), else two 128-thread CTAs per SM
     static const int force_nw = getenv("GPRN_MID_WARPS") ? atoi(getenv("GPRN_MID_WARPS")) : 0;
     const bool wide = force_nw ? force_nw == 8 : h->nt * nmat <= h->num_sms;
+    // more CTAs than are resident at once (two 128-thread CTAs per SM): number them by start order
+    a.ticket = (size_t)h->nt * nmat > 2 * (size_t)h->num_sms ? h->mid_ticket + aux_set : nullptr;
     if (wide) mid_pipeline_kernel<8><<<dim3(h->nt, nmat), 256, MID_SMEM, st>>>(a);
     else mid_pipeline_kernel<4><<<dim3(h->nt, nmat), 128, MID_SMEM, st>>>(a);
     LAUNCH_CHECK(h);
@@ -669,7 +687,9 @@ static int setup_engine(gprn_handle* h, int nslot, Engine& E, bool need_factors 
     if (use_mid_path(h)) {
         // per matrix: tile flags, the z partials [column][row tile][64], the log-det partials [row][lane]
         const size_t nm_ = (size_t)nslot * M;
-        if (ensure_zeroed(h->mid_state, nm_ * MID_TILES * sizeof(int))) return 1;     // flags: zero between launches (mid_finish_kernel)
+        // flags (zero between launches: mid_finish_kernel) + the two start-order tickets (iteration / set-up stream)
+        if (ensure_zeroed(h->mid_state, (nm_ * MID_TILES + 2) * sizeof(int))) return 1;
+        h->mid_ticket = (int*)h->mid_state.p + nm_ * MID_TILES;
         if (ensure(h->mid_zp, nm_ * (size_t)MID_MAX_NT * MID_MAX_NT * NB * sizeof(double))) return 1;
         if (ensure(h->mid_ld, nm_ * MID_MAX_NT * 32 * sizeof(double))) return 1;
     }
@@ -773,7 +793,7 @@ static int launch_setup(gprn_handle* h, Engine& E, int nf, ChainView cs, cudaStr
     } else if (use_mid_path(h)) {
         // q > 1: the cross-node terms and the prior's quadratic forms need L_K^-1 (transposed tiles) and diag(K^-1)
         if (mid_batch(h, E.K, E.W, q > 1 ? E.XK : E.X, E.d_fida, nf * M, nullptr, nullptr, nullptr, q > 1 ? c.gK : nullptr,
-                      c.logdetK, c.mstatus, q > 1 ? 1 : 0, st)) return 1;
+                      c.logdetK, c.mstatus, q > 1 ? 1 : 0, st, aux_set)) return 1;
     } else {
         form_a_kernel<<<dim3(ntri, nf * M), 256, 0, st>>>(E.W, E.K, nullptr, E.d_fida, Np);
         LAUNCH_CHECK(h);
@@ -868,7 +888,7 @@ static int launch_iteration(gprn_handle* h, Engine& E, int na, cudaStream_t st, 
 // single iteration.  GPRN_NO_LOOP=1 falls back to one graph launch + poll per iteration.
 static bool use_device_loop(const gprn_handle* h) {
     static const bool off = getenv("GPRN_NO_LOOP") != nullptr || getenv("GPRN_NO_GRAPH") != nullptr;
-    return !off && !g_debug_sync && !g_profile && !h->loop_unavailable && use_mid_path(h);
+    return !off && !g_debug_sync && !g_profile && !h->loop_unavailable && use_mid_path(h) && h->mid_latency;
 }
 static int iteration_loop_graph(gprn_handle* h, Engine& E, int na, cudaStream_t st) {
     const unsigned char* eb = reinterpret_cast<const unsigned char*>(&E);
@@ -931,7 +951,9 @@ static int iteration_loop_graph(gprn_handle* h, Engine& E, int na, cudaStream_t 
 static int iteration_graph(gprn_handle* h, Engine& E, int na, cudaStream_t st) {
     static const bool no_graph = getenv("GPRN_NO_GRAPH") != nullptr;
     // the fused small path is a handful of launches per iteration and its active count changes every round
-    if (no_graph || g_debug_sync || g_profile || use_small_path(h)) return launch_iteration(h, E, na, st, 0);
+    // (and so is the dataflow path in throughput mode)
+    if (no_graph || g_debug_sync || g_profile || use_small_path(h) || (use_mid_path(h) && !h->mid_latency))
+        return launch_iteration(h, E, na, st, 0);
     // cached graphs hold raw workspace pointers and the context by value: they are valid for exactly this Engine
     const unsigned char* eb = reinterpret_cast<const unsigned char*>(&E);
     if (h->graph_sig.size() != sizeof(Engine) || memcmp(h->graph_sig.data(), eb, sizeof(Engine)) != 0) {
@@ -1043,7 +1065,7 @@ static int run_pool(gprn_handle* h, Engine& E, PoolJob& job, cudaStream_t st) {
             // convergence poll: the one host round trip of a round (of a whole run of rounds with the device loop).
             // iters | status | active are contiguous: one copy brings the iteration counts along.
             CU(cudaMemcpyAsync(h->h_active, c.iters, sizeof(int) * 3 * S, cudaMemcpyDeviceToHost, st));
-            if (use_mid_path(h)) {
+            if (use_mid_path(h) && h->mid_latency) {
                 // latency path: the evaluation is a few milliseconds and the caller waits for it -- spin on the stream
                 // instead of a blocking wait, whose wake-up after a multi-millisecond sleep costs up to 0.5 ms
                 cudaError_t qe;
@@ -1132,6 +1154,7 @@ static int elbo_impl(gprn_handle* h, int64_t B, const double* hyper, bool hyper_
         const int cap0 = max_slots > 0 ? max_slots : h->max_slots;
         const int64_t in_flight = cap0 > 0 ? std::min<int64_t>(B, cap0) : B;
         h->mid_mode = decide_mid_path(h, in_flight);
+        h->mid_latency = h->mid_mode && mid_colocated(h, in_flight);
         h->small_mode = !h->mid_mode && decide_small_path(h, in_flight);
     }
     int nslot = chunk_size(h, B);

@@ -17,9 +17,11 @@
 //       is complete inside the CTA; the column sums that make up z = X v are written per (column, row tile).
 //   mid_finish_kernel, grid = (nt, matrices): adds the z partials and the per-row log-det partials in a fixed order
 //     and forms u_c = sum_{i >= c} Y_ic z_i.
-// Dependencies only point to CTAs with a smaller blockIdx.x of the same matrix (Cholesky) or to Cholesky tiles
-// (inverse), and the host only takes this path when all CTAs of a launch are co-resident, so the flag waits cannot
-// deadlock; they are bounded anyway (a protocol error becomes mstatus = 2, not a hung GPU).
+// Dependencies only point to CTAs with a smaller tile row of the same matrix (Cholesky) or to Cholesky tiles
+// (inverse).  While all CTAs of a launch are co-resident (the latency case) that is enough; a launch with more CTAs
+// than the GPU holds (throughput mode: tens of walkers at N ~ 500, q > 1 batches) numbers its CTAs by a start-order
+// ticket instead of the block index, so a CTA only ever waits for CTAs that started before it.  The waits are bounded
+// anyway (a protocol error becomes mstatus = 2, not a hung GPU).
 // Same building blocks and the same summation orders as small.cuh: an evaluation gives bit-identical results whether
 // it runs alone (this path) or inside a large batch (small.cuh) -- tests/test_gpu_parity.py::test_c3_full_size_properties.
 #pragma once
@@ -49,6 +51,7 @@ struct MidArgs {
     double* zp;            // [id][MID_MAX_NT (column)][MID_MAX_NT (row tile)][64] column sums of Y_ic weighted by v_c
     double* ldpart;        // [id][MID_MAX_NT][32] per-row, per-lane log-det partials (summed as small.cuh sums them)
     int do_inverse;
+    int* ticket;           // null, or a counter (zero at launch, reset by mid_finish_kernel) that orders the CTAs
 };
 
 __device__ __forceinline__ int mid_tile_index(int I, int J) { return I * (I + 1) / 2 + J; }
@@ -139,8 +142,19 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) mid_pipeline_kernel(
     const int tid = threadIdx.x, w4 = (tid >> 5) & 3, lane = tid & 31;
     const bool compute = tid < 128;                    // the four warps that own the 16 x 64 slabs of a tile
     const int r = lane >> 2, c = lane & 3;
-    const int me = blockIdx.x;                         // tile row (Cholesky) / tile column (inverse)
-    const int id = a.ids[blockIdx.y];
+    // Which (tile row, matrix) this CTA works on.  All CTAs co-resident: its block index.  More CTAs than fit on the
+    // GPU at once (throughput mode): the order in which the CTAs START, taken from a ticket counter -- the rows a CTA
+    // waits for then belong to CTAs that have started before it, whatever order the hardware dispatches blocks in, so
+    // the flag waits cannot deadlock.
+    int me = blockIdx.x, mat = blockIdx.y;
+    if (a.ticket) {
+        __shared__ int s_ticket;
+        if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1);
+        __syncthreads();
+        me = s_ticket % (int)gridDim.x;                // tile row (Cholesky) / tile column (inverse)
+        mat = s_ticket / (int)gridDim.x;
+    }
+    const int id = a.ids[mat];
     const double* Km = a.K + (size_t)id * Np * Np;
     double* Wm = a.W + (size_t)id * Np * Np;
     double* Xm = a.X + (size_t)id * Np * Np;
@@ -350,6 +364,7 @@ __global__ void __launch_bounds__(256) mid_finish_kernel(MidArgs a) {
     const int id = a.ids[blockIdx.y];
     // the pipeline launch is over: its tile flags go back to zero for the next one (they are zero when allocated)
     if (me == 0 && tid >= 64 && tid < 64 + MID_TILES) a.tstate[(size_t)id * MID_TILES + tid - 64] = 0;
+    if (a.ticket && me == 0 && blockIdx.y == 0 && tid == 0) *a.ticket = 0;
     if (me == 0 && tid < 32) {         // lane-wise over the rows, then the warp butterfly: the order of small.cuh
         double s = 0.0;
         for (int r = 0; r < nt; r++) s += a.ldpart[((size_t)id * MID_MAX_NT + r) * 32 + tid];
