@@ -172,7 +172,7 @@ static bool decide_small_path(const gprn_handle* h, int64_t sets_in_flight) {
 // of the batch -- post_kernel's block sums depend on it.
 static int vec_threads(const gprn_handle* h) { return std::min(1024, std::max(256, h->Np)); }
 
-// Latency path (mid.cuh): N <= 512 and so few matrices in flight that every CTA of a launch (nt per matrix) is
+// Latency path (mid.cuh): N <= 1024 and so few matrices in flight that every CTA of a launch (nt per matrix) is
 // resident at once -- a single ELBOcalc, a handful of walkers.  One matrix is then worked on by nt CTAs coupled by
 // tile flags instead of by one CTA (small.cuh) or ~20 dependent launches (factor.cuh).  Any q: for q > 1 the set-up
 // also inverts chol(K) (transposed tiles, read by cross_frob_kernel<true> and mid_trmv_lower_kernel).
@@ -183,7 +183,8 @@ static bool mid_colocated(const gprn_handle* h, int64_t sets_in_flight) {
 }
 static bool decide_mid_path(const gprn_handle* h, int64_t sets_in_flight) {
     if (h->nt > MID_MAX_NT || getenv("GPRN_NO_MID") != nullptr) return false;
-    if (mid_colocated(h, sets_in_flight)) return true;                 // latency mode
+    if (mid_colocated(h, sets_in_flight)) return true;                 // latency mode (N <= 1024)
+    if (h->nt > 8) return false;       // 512 < N <= 1024 in batches: the GEMM-based kernels of factor.cuh
     // throughput mode (CTAs numbered by start order): wherever the fused single-CTA kernel does not apply -- q > 1, or
     // 256 < N <= 512 with too few matrices to give every SM two -- instead of the ~20 dependent launches per matrix
     // of factor.cuh.  GPRN_MID_COLOCATED_ONLY=1 restores the multi-kernel path there.

@@ -1,4 +1,4 @@
-// mid.cuh -- latency path for FEW small / mid-size matrices (Np <= 512, q == 1): one matrix is factored and inverted
+// mid.cuh -- dataflow kernels for small / mid-size matrices (Np <= 1024, any q): one matrix is factored and inverted
 // by nt CTAs at once, coupled by per-tile flags in global memory (dataflow), instead of by one CTA walking all tiles
 // (small.cuh: the throughput path for thousands of matrices) or by ~20 dependent launches per matrix (factor.cuh).
 // This is the single-evaluation case -- one ELBOcalc inside an optimiser or sampler step (BASELINE configs C1 / C2) --
@@ -30,7 +30,7 @@
 
 namespace gprn {
 
-#define MID_MAX_NT 8
+#define MID_MAX_NT 16
 #define MID_TILES (MID_MAX_NT * (MID_MAX_NT + 1) / 2)
 // P (potrf64 / L_kk / L_ii) + Bm (B operand, two buffers) + col(128) + pivs(64) + rd(64) + gacc(64) + zpart(4 x 64)
 #define MID_SMEM ((3 * NB * LDT + 4 * NB + NB + 4 * NB) * sizeof(double))
@@ -98,6 +98,53 @@ __device__ __forceinline__ void mid_publish(int* flags, int idx, int value) {
 // products of step t.  ready(t) returns, for all threads and behind a CTA barrier, once B_t may be read (the flag of
 // another CTA's tile, or nothing for an own tile); that barrier also retires the last reader of the buffer about to
 // be overwritten and orders this CTA's own earlier tile stores before the loads.
+// mma_slab_ga with the A fragments of the first four k-steps handed in (`an`, loaded by the previous call or by
+// mid_a_prefetch) and, while the last chunk is being multiplied, the first four k-steps of the NEXT product's A tile
+// loaded into `an` again (Anext; null: none) -- the L2 latency of a product's first fragments is then hidden behind
+// the previous product instead of following the CTA barrier that precedes every product.  Same DMMA sequence.
+__device__ __forceinline__ void mid_a_prefetch(double (&an)[4][2], const double* __restrict__ Ag, int lda, int w4, int lane) {
+    const double* ap = Ag + (size_t)(w4 * 16 + (lane >> 2)) * lda + (lane & 3);
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int x = 0; x < 2; x++) an[u][x] = __ldcg(ap + (size_t)x * 8 * lda + 4 * u);
+}
+template <bool NEG>
+__device__ __forceinline__ void mma_slab_ga_pf(double (&acc)[2][8][2], double (&an)[4][2], const double* __restrict__ Ag,
+                                               const double* __restrict__ Anext, int lda, const double* __restrict__ Bs,
+                                               int w4, int lane) {
+    const int r = lane >> 2, c = lane & 3;
+    const double* ap = Ag + (size_t)(w4 * 16 + r) * lda + c;
+    const double* bp = Bs + r * LDT + c;
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) {
+        double ac[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int x = 0; x < 2; x++) ac[u][x] = NEG ? -an[u][x] : an[u][x];
+        if (ch < 3) {
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int x = 0; x < 2; x++) an[u][x] = __ldcg(ap + (size_t)x * 8 * lda + 16 * (ch + 1) + 4 * u);
+        } else if (Anext) {
+            mid_a_prefetch(an, Anext, lda, w4, lane);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k0 = 16 * ch + 4 * u;
+            double b[8];
+#pragma unroll
+            for (int y = 0; y < 8; y++) b[y] = bp[y * 8 * LDT + k0];
+#pragma unroll
+            for (int x = 0; x < 2; x++)
+#pragma unroll
+                for (int y = 0; y < 8; y++) dmma884(acc[x][y], ac[u][x], b[y]);
+        }
+    }
+}
+
 // NTHR threads stage the B tiles; the warps with `compute` set (the four slab owners) multiply.
 template <int NTHR, class FA, class FB, class FR>
 __device__ __forceinline__ void mid_products(double (&acc)[2][8][2], int t0, int t1, FA a_tile, FB b_tile, FR ready,
@@ -106,6 +153,8 @@ __device__ __forceinline__ void mid_products(double (&acc)[2][8][2], int t0, int
     ready(t0);
     load_tile<false, false>(Bm, b_tile(t0), Np, tid, NTHR);
     cp_async_commit();
+    double an[4][2];
+    if (compute) mid_a_prefetch(an, a_tile(t0), Np, w4, lane);
     for (int t = t0; t < t1; t++) {
         const int s = t - t0;
         if (t + 1 < t1) {
@@ -117,7 +166,8 @@ __device__ __forceinline__ void mid_products(double (&acc)[2][8][2], int t0, int
             cp_async_wait<0>();
         }
         __syncthreads();
-        if (compute) mma_slab_ga<true>(acc, a_tile(t), Np, Bm + (s & 1) * NB * LDT, w4, lane);
+        if (compute)
+            mma_slab_ga_pf<true>(acc, an, a_tile(t), t + 1 < t1 ? a_tile(t + 1) : nullptr, Np, Bm + (s & 1) * NB * LDT, w4, lane);
     }
     __syncthreads();
 }

@@ -34,18 +34,18 @@ def main():
                      [meanfunc.Constant(0.0)] * p, [0.1] * p)
     L = _lib.lib()
     L.gprn_trace_mid_phases.argtypes = [ctypes.POINTER(ctypes.c_ulonglong)]
-    buf = (ctypes.c_ulonglong * 128)()
+    buf = (ctypes.c_ulonglong * 256)()
     g.ELBOcalc()
     _lib.check(L.gprn_trace_mid_phases(buf))       # reset after the warm-up
     _, _, _, it = g.ELBOcalc()
     _lib.check(L.gprn_trace_mid_phases(buf))
-    ph = np.array(list(buf), dtype=np.float64).reshape(2, 8, 8)
+    ph = np.array(list(buf), dtype=np.float64).reshape(2, 16, 8)
     names = ["other", "flag waits", "K loads", "products", "potrf64", "solves", "stores+publish", "inverse reductions"]
     M = 1 + p
     for mode, label, launches in ((0, "set-up launch (Cholesky only)", M), (1, "iteration launches (Cholesky + inverse)", it * M)):
         print(f"{label}: thread-0 microseconds per CTA by phase ({launches} matrices)")
         print("   row " + " ".join(f"{n[:9]:>10s}" for n in names) + "      total")
-        for r in range(8):
+        for r in range((N + 63) // 64):
             us = ph[mode, r] / launches / 1965.0
             print(f"   {r:3d} " + " ".join(f"{v:10.1f}" for v in us) + f" {us.sum():10.1f}")
     g.close()
