@@ -1,22 +1,27 @@
 // mid.cuh -- dataflow kernels for small / mid-size matrices (Np <= 1024, any q): one matrix is factored and inverted
-// by nt CTAs at once, coupled by per-tile flags in global memory (dataflow), instead of by one CTA walking all tiles
-// (small.cuh: the throughput path for thousands of matrices) or by ~20 dependent launches per matrix (factor.cuh).
-// This is the single-evaluation case -- one ELBOcalc inside an optimiser or sampler step (BASELINE configs C1 / C2) --
-// where the GPU holds M = q(p+1) matrices and the evaluation is ONE dependency chain.
+// by nt CTAs at once, coupled by per-tile flags in global memory, instead of by one CTA walking all tiles (small.cuh:
+// the throughput path for thousands of q = 1 matrices) or by ~20 dependent launches per matrix (factor.cuh).
+// Latency mode: the single-evaluation case -- one ELBOcalc inside an optimiser or sampler step (BASELINE configs C1 /
+// C2) -- where the GPU holds M = q(p+1) matrices, every CTA is resident and the evaluation is ONE dependency chain.
+// Throughput mode: more CTAs than the GPU holds (tens of walkers, q > 1 batches); CTAs numbered by a start-order ticket.
 //
-//   mid_pipeline_kernel, grid = (nt, matrices), 128 threads (four warps = the four 16 x 64 row slabs of a tile):
-//     Cholesky, left-looking: CTA r owns tile ROW r.  For k = 0..r it forms
+//   mid_pipeline_kernel<NW>, grid = (nt, matrices); four warps own the four 16 x 64 row slabs of a tile (NW = 8: four
+//   more warps that only stage tiles and join potrf64):
+//     Cholesky, left-looking: CTA r owns tile ROW r.  For k = 0..r-1 it forms
 //         T_rk = A_rk - sum_{k' < k} L_rk' L_kk'^T
-//       (A fragments straight from its own finished tiles in L2, mma_slab_ga; B tile L_kk' of CTA k through shared
-//       memory, after that tile's flag is up), then factors the diagonal tile (k == r, potrf64) or solves against
-//       L_kk (flag of CTA k) in registers (trsm_rows_inreg), stores L_rk and raises its flag.
+//       (A fragments straight from its own finished tiles in L2; B tile L_kk' of CTA k through two cp.async buffers
+//       in shared memory, after that tile's flag is up), solves against L_kk (flag of CTA k) in registers
+//       (trsm_rows_inreg), stores L_rk and raises its flag -- and subtracts L_rk L_rk^T from the DIAGONAL tile's own
+//       accumulator at once, so that after the row's last solve one product, not r, precedes potrf64.
 //     Inverse, transposed (Y_ij = X_ij^T, see small.cuh): CTA c owns tile COLUMN c,
 //         Y_ic L_ii^T = [i == c] I - sum_{k=c}^{i-1} Y_kc L_ik^T ,   i = c .. nt-1,
 //       whose only inputs from other CTAs are Cholesky tiles (flags) -- the columns of the inverse are independent
-//       chains.  Y goes to the X buffer (L tiles are still being read by the other columns).  g_c (row sums of squares)
-//       is complete inside the CTA; the column sums that make up z = X v are written per (column, row tile).
-//   mid_finish_kernel, grid = (nt, matrices): adds the z partials and the per-row log-det partials in a fixed order
-//     and forms u_c = sum_{i >= c} Y_ic z_i.
+//       chains.  While L_ii is not there yet the CTA works ahead on row i + 1 in a second accumulator.  Y goes to the X
+//       buffer (L tiles are still being read by the other columns).  g_c (row sums of squares) is complete inside the
+//       CTA; the column sums that make up z = X v are written per (column, row tile).
+//   mid_finish_kernel, grid = (nt, matrices): adds the z partials and the per-row log-det partials in a fixed order,
+//     forms u_c = sum_{i >= c} Y_ic z_i and resets the flags (and the ticket) for the next launch.
+//   mid_trmv_lower_kernel: z = X v on transposed tiles (prior quadratic forms, q > 1).
 // Dependencies only point to CTAs with a smaller tile row of the same matrix (Cholesky) or to Cholesky tiles
 // (inverse).  While all CTAs of a launch are co-resident (the latency case) that is enough; a launch with more CTAs
 // than the GPU holds (throughput mode: tens of walkers at N ~ 500, q > 1 batches) numbers its CTAs by a start-order
