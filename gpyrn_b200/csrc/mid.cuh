@@ -278,9 +278,13 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) mid_pipeline_kernel(
             slab_store(acc, MID_TILE(Wm, me, k), Np, w4, lane);
             slab_store(acc, Bm, LDT, w4, lane);        // and kept on chip: both operands of the diagonal update
         }
-        mid_publish(flags, mid_tile_index(me, k), 1);
+        // the diagonal update comes first -- it is what potrf64 of this row waits for -- while the global stores of
+        // L_me,k drain; the flag follows (the other rows have the time of a potrf64 to spare before they need the tile)
+        __syncthreads();
         MID_PH(3);
         if (compute) mma_slab<true>(accd, Bm, Bm, w4, lane);      // the DMMA sequence of mma_slab_ga: same bits
+        MID_PH(6);
+        mid_publish(flags, mid_tile_index(me, k), 1);
     }
     {
         MID_PH(4);
