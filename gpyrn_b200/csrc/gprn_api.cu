@@ -899,6 +899,7 @@ static int iteration_loop_graph(gprn_handle* h, Engine& E, int na, cudaStream_t 
     }
     auto it = h->loop_graphs.find(na);
     if (it == h->loop_graphs.end()) {
+        if (h->loop_graphs.size() >= 64) return 2;       // many distinct counts: per-iteration launches for the rest
         cudaGraph_t g = nullptr;
         CU(cudaGraphCreate(&g, 0));
         cudaGraphConditionalHandle cond;

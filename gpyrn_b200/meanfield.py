@@ -726,16 +726,21 @@ class inference:
         self.set_parameters(results[best].x)
         return results
 
-    def logposterior_batch(self, thetas, priors, names=None, max_iter=100):
+    def logposterior_batch(self, thetas, priors, names=None, max_iter=100, rows=None):
         """Vectorised log-posterior for ensemble samplers (emcee ``vectorize=True``): rows of ``thetas`` are walker
         positions in the free parameters; returns (log prior + ELBO, ELBO), each (B,).  One ``ELBO_batch`` call for
         the rows with a finite prior, capped at ``max_iter`` iterations like the reference's ``logposterior``
-        (:1214-1219), warm-started per row from the device-resident chain state."""
+        (:1214-1219), warm-started per row from the device-resident chain state.  ``rows``: evaluate only these
+        row indices (the others come back as -inf) -- an ensemble sampler that moves half of its walkers passes the
+        whole ensemble and the moving half, so that row = walker = chain on the device."""
         self._require_components()
         thetas = np.atleast_2d(np.asarray(thetas, dtype=float))
         if names is None:
             names = np.array(list(self.parameters_dict.keys()))[~self.frozen_mask]
-        lp = np.array([sum(priors[n].logpdf(v) for v, n in zip(row, names)) for row in thetas], dtype=float)
+        lp = np.full(thetas.shape[0], -np.inf)
+        todo = range(thetas.shape[0]) if rows is None else [int(r) for r in rows]
+        for r in todo:
+            lp[r] = sum(priors[n].logpdf(v) for v, n in zip(thetas[r], names))
         ok = np.isfinite(lp)
         elbo = np.full(thetas.shape[0], -np.inf)
         if ok.any():
@@ -748,28 +753,68 @@ class inference:
         total = np.where(ok, lp + elbo, -np.inf)
         return total, elbo
 
-    def mcmc(self, priors, p0=None, vars=None, niter=500, **kwargs):
-        """Posterior sampling of the hyper-parameters with emcee (the sampler itself is a host driver
-        outside this package's scope; it needs the optional ``emcee`` dependency)."""
-        try:
-            from emcee import EnsembleSampler
-        except ImportError as e:
-            raise ImportError('inference.mcmc needs the optional dependency `emcee`') from e
+    def mcmc(self, priors, p0=None, vars=None, niter=500, filename="gprn.npz", seed=None, **kwargs):
+        """Posterior sampling of the free hyper-parameters with an affine-invariant ensemble sampler
+        (reference :1154-1286: ``2 * ndim`` walkers, log-posterior = log prior + ELBO capped at 100 iterations, the ELBO
+        kept as blob, autocorrelation-time convergence check every 10 steps).
+
+        The walkers that move in a half step are ONE batched device call (``logposterior_batch``), each warm-started
+        from its own device-resident variational state.  The sampler is ``gpyrn_b200.sampler.EnsembleSampler`` (the
+        stretch move of emcee's default configuration, which the reference uses; emcee itself is not needed); the
+        chain is written to ``filename`` as ``.npz`` (the reference's HDF5 backend needs h5py; ``None``: no file).
+        Returns the sampler (``get_chain``, ``get_log_prob``, ``get_blobs``, ``acceptance_fraction``,
+        ``get_autocorr_time`` as in emcee).  ``kwargs`` go to the sampler (``a``)."""
+        from .sampler import EnsembleSampler, NpzBackend
         self._require_components()
+        if vars is not None and not isinstance(vars, (str, list)):
+            raise ValueError(f'`vars` should be str or list, got {type(vars)}')
         self._select_vars(vars)
         names = np.array(list(self.parameters_dict.keys()))[~self.frozen_mask]
+        rng = np.random.default_rng(seed)
 
-        def logposterior(thetas):                 # emcee vectorize=True: (walkers in the move, ndim) -> blobs
-            total, elbo = self.logposterior_batch(thetas, priors, names=names, max_iter=100)
+        def prior_rvs():
+            return np.array([priors[n].rvs(random_state=rng) for n in names])
+
+        def logprior(theta):
+            return sum(priors[n].logpdf(v) for v, n in zip(theta, names))
+
+        def logposterior(coords, rows):           # the whole ensemble + the rows that move: row = walker = chain
+            total, elbo = self.logposterior_batch(coords, priors, names=names, max_iter=100, rows=rows)
             return np.column_stack([total, elbo])
 
         ndim = len(names)
         nwalkers = 2 * ndim
+        print(f'Setting up sampler (parameters: {ndim}, walkers: {nwalkers})')
         if p0 is None:
-            p0 = np.array([[priors[n].rvs() for n in names] for _ in range(nwalkers)])
+            p0 = np.array([prior_rvs() for _ in range(nwalkers)])
+        else:                                      # a small ball around p0, as the reference draws it (:1238-1246)
+            sigma = []
+            for n in names:
+                sd = priors[n].std
+                sigma.append(float(sd() if callable(sd) else sd))
+            # emcee.utils.sample_ellipsoid(p0, covmat, size): normal draws with `diag(sigma) / 100` as COVARIANCE
+            p0 = rng.multivariate_normal(np.asarray(p0, dtype=float), np.diag(sigma) / 100, size=nwalkers)
+            for i, pt in enumerate(p0):
+                if np.isneginf(logprior(pt)):
+                    p0[i] = prior_rvs()
+        print('initial values for parameters are set')
         self.reset_chain_state()
-        sampler = EnsembleSampler(nwalkers, ndim, logposterior, vectorize=True, **kwargs)
-        sampler.run_mcmc(p0, niter, progress=False)
+        backend = NpzBackend(filename) if filename else None
+        sampler = EnsembleSampler(nwalkers, ndim, logposterior, seed=rng.integers(2 ** 31), backend=backend,
+                                  rows_aware=True, **kwargs)
+        old_tau = np.inf
+        for sample in sampler.sample(p0, iterations=niter):
+            if sampler.iteration % 10:
+                continue
+            print(sample.log_prob.max())
+            tau = sampler.get_autocorr_time(tol=0)          # an estimate even if it is not trustworthy yet
+            converged = np.all(tau * 100 < sampler.iteration) & np.all(np.abs(old_tau - tau) / tau < 0.01)
+            if converged:
+                print('MCMC converged!')
+                break
+            old_tau = tau
+        if backend is not None and sampler.iteration:
+            backend.save(sampler, force=True)
         return sampler
 
     # ------------------------------------------------------------------------------------------
