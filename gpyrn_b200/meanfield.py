@@ -780,7 +780,8 @@ class inference:
 
         def logposterior(coords, rows):           # the whole ensemble + the rows that move: row = walker = chain
             total, elbo = self.logposterior_batch(coords, priors, names=names, max_iter=100, rows=rows)
-            return np.column_stack([total, elbo])
+            bad = np.isnan(total)                 # a covariance matrix that is not positive definite: reject the move
+            return np.column_stack([np.where(bad, -np.inf, total), np.where(bad, -np.inf, elbo)])
 
         ndim = len(names)
         nwalkers = 2 * ndim
