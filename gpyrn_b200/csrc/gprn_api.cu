@@ -887,16 +887,27 @@ static int launch_iteration(gprn_handle* h, Engine& E, int na, cudaStream_t st, 
 // with no host round trip until there is something to retire -- for a single evaluation: the whole fixed-point loop
 // of ELBOcalc (meanfield.py:634-646) in one launch.  The host then polls, retires and refills exactly as after a
 // single iteration.  GPRN_NO_LOOP=1 falls back to one graph launch + poll per iteration.
+// Cached graphs hold raw workspace pointers, the context by value and the kernel choice of the call that captured them:
+// they are valid for exactly this Engine and this path (the path can change under the same Engine when an experiment
+// switch such as GPRN_NO_MID is toggled between calls).  Drops the cache when either differs.
+static void check_graph_signature(gprn_handle* h, const Engine& E) {
+    const unsigned char* eb = reinterpret_cast<const unsigned char*>(&E);
+    const unsigned char mode[3] = {(unsigned char)h->mid_mode, (unsigned char)h->small_mode, (unsigned char)h->mid_latency};
+    const size_t n = sizeof(Engine) + sizeof(mode);
+    if (h->graph_sig.size() != n || memcmp(h->graph_sig.data(), eb, sizeof(Engine)) != 0 ||
+        memcmp(h->graph_sig.data() + sizeof(Engine), mode, sizeof(mode)) != 0) {
+        drop_graphs(h);
+        h->graph_sig.assign(eb, eb + sizeof(Engine));
+        h->graph_sig.insert(h->graph_sig.end(), mode, mode + sizeof(mode));
+    }
+}
+
 static bool use_device_loop(const gprn_handle* h) {
     static const bool off = getenv("GPRN_NO_LOOP") != nullptr || getenv("GPRN_NO_GRAPH") != nullptr;
     return !off && !g_debug_sync && !g_profile && !h->loop_unavailable && use_mid_path(h) && h->mid_latency;
 }
 static int iteration_loop_graph(gprn_handle* h, Engine& E, int na, cudaStream_t st) {
-    const unsigned char* eb = reinterpret_cast<const unsigned char*>(&E);
-    if (h->graph_sig.size() != sizeof(Engine) || memcmp(h->graph_sig.data(), eb, sizeof(Engine)) != 0) {
-        drop_graphs(h);
-        h->graph_sig.assign(eb, eb + sizeof(Engine));
-    }
+    check_graph_signature(h, E);
     auto it = h->loop_graphs.find(na);
     if (it == h->loop_graphs.end()) {
         if (h->loop_graphs.size() >= 64) return 2;       // many distinct counts: per-iteration launches for the rest
@@ -957,11 +968,7 @@ static int iteration_graph(gprn_handle* h, Engine& E, int na, cudaStream_t st) {
     if (no_graph || g_debug_sync || g_profile || use_small_path(h) || (use_mid_path(h) && !h->mid_latency))
         return launch_iteration(h, E, na, st, 0);
     // cached graphs hold raw workspace pointers and the context by value: they are valid for exactly this Engine
-    const unsigned char* eb = reinterpret_cast<const unsigned char*>(&E);
-    if (h->graph_sig.size() != sizeof(Engine) || memcmp(h->graph_sig.data(), eb, sizeof(Engine)) != 0) {
-        drop_graphs(h);
-        h->graph_sig.assign(eb, eb + sizeof(Engine));
-    }
+    check_graph_signature(h, E);
     auto it = h->iter_graphs.find(na);
     if (it == h->iter_graphs.end()) {
         if (h->iter_graphs.size() >= 64) {          // many distinct counts (large pools of small sets): launch directly
