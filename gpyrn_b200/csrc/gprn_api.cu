@@ -631,8 +631,10 @@ static int mid_batch(gprn_handle* h, const double* K, double* W, double* X, cons
     // one CTA per SM while they all fit (256 threads: potrf64 on eight warps), else two 128-thread CTAs per SM
     static const int force_nw = getenv("GPRN_MID_WARPS") ? atoi(getenv("GPRN_MID_WARPS")) : 0;
     const bool wide = force_nw ? force_nw == 8 : h->nt * nmat <= h->num_sms;
-    // more CTAs than are resident at once (two 128-thread CTAs per SM): number them by start order
-    a.ticket = (size_t)h->nt * nmat > 2 * (size_t)h->num_sms ? h->mid_ticket + aux_set : nullptr;
+    // CTAs are numbered by start order, not by block index: needed when a launch has more CTAs than are resident at
+    // once (throughput mode), and used always -- a set-up launch may share the GPU with an iteration launch, and a
+    // CTA must only ever wait for CTAs that are running (one atomic per CTA, < 1 us per launch)
+    a.ticket = h->mid_ticket + aux_set;
     if (wide) mid_pipeline_kernel<8><<<dim3(h->nt, nmat), 256, MID_SMEM, st>>>(a);
     else mid_pipeline_kernel<4><<<dim3(h->nt, nmat), 128, MID_SMEM, st>>>(a);
     LAUNCH_CHECK(h);

@@ -197,10 +197,10 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) mid_pipeline_kernel(
     const int tid = threadIdx.x, w4 = (tid >> 5) & 3, lane = tid & 31;
     const bool compute = tid < 128;                    // the four warps that own the 16 x 64 slabs of a tile
     const int r = lane >> 2, c = lane & 3;
-    // Which (tile row, matrix) this CTA works on.  All CTAs co-resident: its block index.  More CTAs than fit on the
-    // GPU at once (throughput mode): the order in which the CTAs START, taken from a ticket counter -- the rows a CTA
-    // waits for then belong to CTAs that have started before it, whatever order the hardware dispatches blocks in, so
-    // the flag waits cannot deadlock.
+    // Which (tile row, matrix) this CTA works on: the order in which the CTAs START, taken from a ticket counter --
+    // the rows a CTA waits for then belong to CTAs that have started before it, whatever order the hardware dispatches
+    // blocks in and however many of them are resident, so the flag waits cannot deadlock.  (ticket == null: block
+    // index; only safe when every CTA of the launch is resident.)
     int me = blockIdx.x, mat = blockIdx.y;
     if (a.ticket) {
         __shared__ int s_ticket;
