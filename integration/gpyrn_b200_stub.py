@@ -54,7 +54,10 @@ def program(k):
         return [DOPC[k.k._tag]]
     if name in OPC_BY_CLASS:
         return [OPC_BY_CLASS[name]]
-    return [OPC[k._tag]]
+    tag = getattr(k, "_tag", None)
+    if tag not in OPC:
+        raise NotImplementedError(f"gpyrn.covfunc.{name} has no device program in libgprn_b200")
+    return [OPC[tag]]
 
 
 def _p(a, t=_d):

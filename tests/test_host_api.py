@@ -287,3 +287,31 @@ def test_reference_side_stub_is_syntactically_complete():
     for name in used:
         assert re.search(r"\b" + name + r"\s*\(", hdr), name
     assert {"gprn_create", "gprn_set_model", "gprn_elbo_batched", "gprn_predict"} <= used
+
+
+def test_stub_programs_of_reference_kernel_objects_match_the_package():
+    """The reference-side stub serialises the REFERENCE's kernel objects (by `_tag`, the stationary "other" kernels by
+    class name) into the same postfix programs and parameter vectors as this package's own classes.  CPU only: needs
+    the reference copy under baseline/_ref (made by __graft_entry__.build() in the build container)."""
+    from tests import _ref_shim
+    if not _ref_shim.available():
+        pytest.skip("baseline/_ref/gpyrn not present")
+    _ref_shim.install()
+    from gpyrn import covfunc as ref
+    from integration import gpyrn_b200_stub as stub
+    pairs = [
+        (ref.QuasiPeriodic(1, 30, 27, 0.7) * ref.Matern52(1.0, 40.0) + ref.WhiteNoise(0.1),
+         covfunc.QuasiPeriodic(1, 30, 27, 0.7) * covfunc.Matern52(1.0, 40.0) + covfunc.WhiteNoise(0.1)),
+        (ref.Derivative(ref.SquaredExponential(2.0, 9.0)), covfunc.Derivative(covfunc.SquaredExponential(2.0, 9.0))),
+        (ref.GammaExp(1.1, 1.6, 120.0) * ref.Piecewise(900.0) + ref.Paciorek(0.9, 70.0, 110.0),
+         covfunc.GammaExp(1.1, 1.6, 120.0) * covfunc.Piecewise(900.0) + covfunc.Paciorek(0.9, 70.0, 110.0)),
+        (ref.NewPeriodic(1.0, 2.0, 50.0, 1.5) + ref.QuasiNewPeriodic(1.0, 1.5, 60.0, 25.0, 0.9) * ref.QuasiCosPeriodic(1, 2, 3, 4),
+         covfunc.NewPeriodic(1.0, 2.0, 50.0, 1.5) + covfunc.QuasiNewPeriodic(1.0, 1.5, 60.0, 25.0, 0.9) * covfunc.QuasiCosPeriodic(1, 2, 3, 4)),
+        (ref.RQP(1.0, 1.2, 80.0, 25.0, 0.9) + ref.Constant(0.2) * ref.Cosine(1.0, 9.0) + ref.Exponential(1.0, 50.0),
+         covfunc.RQP(1.0, 1.2, 80.0, 25.0, 0.9) + covfunc.Constant(0.2) * covfunc.Cosine(1.0, 9.0) + covfunc.Exponential(1.0, 50.0)),
+    ]
+    for kr, ko in pairs:
+        assert stub.program(kr) == ko.program()
+        assert np.array_equal(np.ravel(kr.pars).astype(float), ko.pars)
+    with pytest.raises(NotImplementedError):           # CosPeriodic registers only (P, ell) in the reference: not bindable
+        stub.program(ref.CosPeriodic(1.0, 2.0, 3.0))
