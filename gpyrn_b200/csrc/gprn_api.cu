@@ -186,7 +186,7 @@ static bool decide_mid_path(const gprn_handle* h, int64_t sets_in_flight) {
     if (mid_colocated(h, sets_in_flight)) return true;                 // latency mode (N <= 1024)
     if (h->nt > 8) return false;       // 512 < N <= 1024 in batches: the GEMM-based kernels of factor.cuh
     // throughput mode (CTAs numbered by start order): wherever the fused single-CTA kernel does not apply -- q > 1, or
-    // 256 < N <= 512 with too few matrices to give every SM two -- instead of the ~20 dependent launches per matrix
+    // 256 < N <= 512 with fewer than eight matrices per SM -- instead of the ~20 dependent launches per matrix
     // of factor.cuh.  GPRN_MID_COLOCATED_ONLY=1 restores the multi-kernel path there.
     if (getenv("GPRN_MID_COLOCATED_ONLY") != nullptr) return false;
     return !decide_small_path(h, sets_in_flight);
@@ -663,6 +663,8 @@ static size_t per_set_bytes(const gprn_handle* h, bool need_factors) {
     size_t vecs = 8 * M * Np * sizeof(double);
     size_t state = 4 * (size_t)h->d * sizeof(double);
     size_t misc = 4096;
+    if (use_mid_path(h))      // tile flags, z partials [column][row tile][64], log-det partials per matrix (setup_engine)
+        misc += M * (MID_TILES * sizeof(int) + ((size_t)MID_MAX_NT * MID_MAX_NT * NB + MID_MAX_NT * 32) * sizeof(double));
     if (!small && use_two_level(h->Np))
         misc += M * (size_t)(TRTRI_MAXCH(h->Np) - 1) * OUTER_KB * Np * sizeof(double);      // split-K partials of the inverse
     return mats + vecs + state + misc;
