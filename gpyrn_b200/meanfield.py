@@ -753,7 +753,7 @@ class inference:
         total = np.where(ok, lp + elbo, -np.inf)
         return total, elbo
 
-    def mcmc(self, priors, p0=None, vars=None, niter=500, filename="gprn.npz", seed=None, **kwargs):
+    def mcmc(self, priors, p0=None, vars=None, niter=500, filename="gprn.h5", seed=None, **kwargs):
         """Posterior sampling of the free hyper-parameters with an affine-invariant ensemble sampler
         (reference :1154-1286: ``2 * ndim`` walkers, log-posterior = log prior + ELBO capped at 100 iterations, the ELBO
         kept as blob, autocorrelation-time convergence check every 10 steps).
@@ -761,10 +761,12 @@ class inference:
         The walkers that move in a half step are ONE batched device call (``logposterior_batch``), each warm-started
         from its own device-resident variational state.  The sampler is ``gpyrn_b200.sampler.EnsembleSampler`` (the
         stretch move of emcee's default configuration, which the reference uses; emcee itself is not needed); the
-        chain is written to ``filename`` as ``.npz`` (the reference's HDF5 backend needs h5py; ``None``: no file).
+        chain is written to ``filename`` -- ``gprn.h5`` in emcee's HDF5 backend layout like the reference's (:1253-1255;
+        ``gpyrn_b200.h5chain`` writes the container, h5py is not needed), a ``.npz`` archive for any other extension,
+        ``None``: no file.
         Returns the sampler (``get_chain``, ``get_log_prob``, ``get_blobs``, ``acceptance_fraction``,
         ``get_autocorr_time`` as in emcee).  ``kwargs`` go to the sampler (``a``)."""
-        from .sampler import EnsembleSampler, NpzBackend
+        from .sampler import EnsembleSampler, backend_for
         self._require_components()
         if vars is not None and not isinstance(vars, (str, list)):
             raise ValueError(f'`vars` should be str or list, got {type(vars)}')
@@ -800,7 +802,7 @@ class inference:
                     p0[i] = prior_rvs()
         print('initial values for parameters are set')
         self.reset_chain_state()
-        backend = NpzBackend(filename) if filename else None
+        backend = backend_for(filename) if filename else None
         sampler = EnsembleSampler(nwalkers, ndim, logposterior, seed=rng.integers(2 ** 31), backend=backend,
                                   rows_aware=True, **kwargs)
         old_tau = np.inf

@@ -11,7 +11,8 @@ that ``mcmc`` uses, vectorised from the start:
   ``get_chain`` / ``get_log_prob`` / ``get_blobs`` / ``acceptance_fraction`` / ``get_autocorr_time`` follow its meaning.
 * ``integrated_time`` -- the integrated autocorrelation time with Sokal's automatic window (c = 5), the estimator
   behind ``sampler.get_autocorr_time(tol=0)`` that the reference's convergence check polls (:1268-1283).
-* ``NpzBackend`` -- chain, log-probabilities and blobs in a ``.npz`` file (the HDF5 container is not available here).
+* ``HDFBackend`` -- chain, log-probabilities and blobs in emcee's HDF5 layout (``gprn.h5`` of the reference, written by
+  ``gpyrn_b200.h5chain``: h5py is not needed); ``NpzBackend`` -- the same arrays in a ``.npz`` file.
 
 The log-probability function may be *row aware*: it then receives the coordinates of the whole ensemble plus the
 indices of the rows to evaluate, and returns full-length arrays.  ``inference.mcmc`` uses that so that the
@@ -71,8 +72,8 @@ def integrated_time(x, c=5, tol=50, quiet=True):
 
 class NpzBackend:
     """Chain storage in one ``.npz`` file: ``chain`` (nsteps, nwalkers, ndim), ``log_prob`` (nsteps, nwalkers),
-    ``blobs`` (nsteps, nwalkers, nblobs), ``accepted`` (nwalkers,), ``iteration``.  Stands in for emcee's HDF5 backend
-    of the reference (``gprn.h5``, meanfield.py:1253-1255)."""
+    ``blobs`` (nsteps, nwalkers, nblobs), ``accepted`` (nwalkers,), ``iteration``.  The numpy-native alternative to
+    :class:`HDFBackend`."""
 
     def __init__(self, filename="gprn.npz", every=50):
         self.filename = filename
@@ -94,6 +95,43 @@ class NpzBackend:
     def load(filename):
         z = np.load(filename)
         return {k: z[k] for k in z.files}
+
+
+class HDFBackend(NpzBackend):
+    """The reference's chain file: emcee's ``HDFBackend`` layout in an HDF5 container (``gprn.h5``,
+    meanfield.py:1253-1255) -- group ``name`` with the attributes ``version`` / ``nwalkers`` / ``ndim`` / ``has_blobs`` /
+    ``iteration`` and the datasets ``accepted``, ``chain``, ``log_prob``, ``blobs``.  Written by
+    ``gpyrn_b200.h5chain`` (no h5py in this image): contiguous datasets, the file is rewritten at every save.  Like the
+    reference's ``be.reset(nwalkers, ndim)``, ``reset`` empties the file."""
+
+    def __init__(self, filename="gprn.h5", name="mcmc", every=50):
+        super().__init__(filename, every)
+        self.name = name
+
+    def reset(self, nwalkers, ndim):
+        from .h5chain import write_chain
+        super().reset(nwalkers, ndim)
+        write_chain(self.filename, np.zeros((0, self.nwalkers, self.ndim)), np.zeros((0, self.nwalkers)),
+                    np.zeros(self.nwalkers), name=self.name)
+
+    def save(self, sampler, force=False):
+        from .h5chain import write_chain
+        if not force and sampler.iteration % self.every:
+            return
+        write_chain(self.filename, sampler.get_chain(), sampler.get_log_prob(), sampler.naccepted, sampler.get_blobs(),
+                    name=self.name)
+
+    @staticmethod
+    def load(filename, name="mcmc"):
+        from .h5chain import read_chain
+        return read_chain(filename, name)
+
+
+def backend_for(filename, **kwargs):
+    """``.h5`` / ``.hdf5`` -> :class:`HDFBackend` (the reference's format), anything else -> :class:`NpzBackend`."""
+    if str(filename).lower().endswith(('.h5', '.hdf5', '.hdf')):
+        return HDFBackend(filename, **kwargs)
+    return NpzBackend(filename, **kwargs)
 
 
 class EnsembleSampler:
