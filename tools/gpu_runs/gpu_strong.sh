@@ -1,5 +1,5 @@
 #!/bin/bash
-# strong-scaling point: bash tools/gpu_strong.sh N   (128 natural-order C4 sets, 6 in flight per GPU)
+# strong-scaling point: bash tools/gpu_runs/gpu_strong.sh N   (128 natural-order C4 sets, 6 in flight per GPU)
 N=$1
 mkdir -p gpurun_out
 if [ "$N" = "1" ]; then CMD="python"; else CMD="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29561"; fi
