@@ -155,8 +155,8 @@ class H5Writer:
             heap += _pad8(name.encode('ascii') + b'\0')
         free_at = len(heap)
         heap += struct.pack('<QQ', 1, 32) + b'\0' * 16                         # next free block: none (1); size 32
-        heap_data = self._alloc(bytes(heap))
-        heap_addr = self._alloc(b'HEAP' + struct.pack('<B3xQQQ', 0, len(heap), free_at, heap_data))
+        self._out += b'\0' * (-len(self._out) % 8)                              # prefix, data segment right behind it
+        heap_addr = self._alloc(b'HEAP' + struct.pack('<B3xQQQ', 0, len(heap), free_at, len(self._out) + 32) + bytes(heap))
         # symbol nodes of up to 2*_LEAF_K entries each, then one leaf-level B-tree node over them
         keys, nodes = [0], []
         for s in range(0, len(entries), 2 * _LEAF_K):
