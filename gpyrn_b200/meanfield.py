@@ -24,6 +24,40 @@ import numpy as np
 from . import _lib, covfunc, meanfunc
 
 
+_chol_handles = {}                       # device ordinal -> scratch `inference` whose handle runs _cholNugget
+_chol_lock = threading.Lock()
+
+
+def _cholNugget(matrix, device=0):
+    """
+    Cholesky decomposition of a symmetric positive definite matrix (reference ``_cholNugget``, meanfield.py:71-88).
+
+    The factorisation runs in the blocked device kernels of ``csrc/factor.cuh`` -- the ones every ELBO iteration and
+    prediction uses -- through ``gprn_debug_factor``; only the lower triangle of ``matrix`` is
+    read.  As in the reference no nugget is added, and a matrix that is not positive definite gives a NaN factor
+    (what ``jnp.linalg.cholesky`` returns) instead of raising.
+
+    Returns:
+        L (n, n) lower-triangular factor, nugget (always 0.0)
+    """
+    A = _lib.f64(matrix)
+    if A.ndim != 2 or A.shape[0] != A.shape[1] or A.shape[0] < 1:
+        raise ValueError(f'_cholNugget: expected a square matrix, got shape {A.shape}')
+    n = A.shape[0]
+    L = np.empty((n, n))
+    with _chol_lock:
+        g = _chol_handles.get(device)
+        if g is None:
+            g = _chol_handles[device] = inference(1, np.arange(4.0), np.zeros(4), np.ones(4), device=device)
+        rc = _lib.lib().gprn_debug_factor(g._h(), n, _lib.dptr(A), _lib.dptr(L), None, None)
+        if rc != 0:
+            msg = _lib.lib().gprn_last_error().decode()
+            if 'not positive definite' not in msg:
+                raise _lib.GprnError(msg)
+            L.fill(np.nan)
+    return L, 0.0
+
+
 class inference:
     """
     Mean-field variational inference for GPRNs.
