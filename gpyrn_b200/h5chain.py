@@ -114,7 +114,7 @@ class H5Writer:
         return parent.children.setdefault(name, _Group())
 
     def dataset(self, parent, name, array):
-        (parent or self.root).children[name] = np.ascontiguousarray(array)
+        (parent or self.root).children[name] = np.array(array, order='C')       # (ascontiguousarray would make scalars 1-d)
 
     def attr(self, parent, name, value):
         (parent or self.root).attrs[name] = value

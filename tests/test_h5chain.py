@@ -127,3 +127,54 @@ def test_hdf_backend_of_the_sampler(tmp_path):
     assert d["iteration"] == 30 and d["nwalkers"] == 4 and d["ndim"] == 2 and d["has_blobs"]
     assert np.array_equal(d["chain"], s.get_chain()) and np.array_equal(d["log_prob"], s.get_log_prob())
     assert np.array_equal(d["blobs"], s.get_blobs()[:, :, 0]) and np.array_equal(d["accepted"], s.naccepted)
+
+
+def test_round_trip_of_random_trees():
+    """Property test: random group trees with float / integer / boolean datasets and attributes of random shapes come
+    back from the reader exactly as written (names in byte order, empty arrays, scalars, nesting three levels deep)."""
+    from hypothesis import given, settings, strategies as st
+    from hypothesis.extra import numpy as hnp
+
+    names = st.text(alphabet="abcdefghijklmnopqrstuvwxyz_0123456789", min_size=1, max_size=12)
+    arrays = st.one_of(
+        hnp.arrays(np.float64, hnp.array_shapes(min_dims=0, max_dims=3, min_side=0, max_side=5),
+                   elements=st.floats(allow_nan=False, width=64)),
+        hnp.arrays(np.int64, hnp.array_shapes(min_dims=1, max_dims=2, min_side=0, max_side=6)),
+        hnp.arrays(np.bool_, hnp.array_shapes(min_dims=0, max_dims=1, min_side=1, max_side=4)))
+    attrs = st.dictionaries(names, st.one_of(arrays, st.text(alphabet="abcXYZ .-", max_size=9)), max_size=3)
+    leaf = st.fixed_dictionaries({"attrs": attrs, "data": st.dictionaries(names, arrays, max_size=10)})
+    tree = st.recursive(leaf, lambda kids: st.fixed_dictionaries(
+        {"attrs": attrs, "data": st.dictionaries(names, arrays, max_size=4), "groups": st.dictionaries(names, kids, max_size=3)}),
+        max_leaves=6)
+
+    def put(w, g, node):
+        for k, v in node["attrs"].items():
+            w.attr(g, k, v)
+        for k, v in node["data"].items():
+            w.dataset(g, k, v)
+        for k, v in node.get("groups", {}).items():
+            if k not in node["data"]:
+                put(w, w.group(k, g if g is not None else w.root), v)
+
+    def same(a, b):
+        a, b = np.asarray(a), np.asarray(b)
+        return a.shape == b.shape and a.dtype.kind == b.dtype.kind and np.array_equal(a, b)
+
+    def check(r, node):
+        for k, v in node["attrs"].items():
+            assert (r.attrs[k] == v) if isinstance(v, str) else same(r.attrs[k], v)
+        for k, v in node["data"].items():
+            assert r.children[k].children is None and same(r.children[k].data, v)
+        sub = {k: v for k, v in node.get("groups", {}).items() if k not in node["data"]}
+        assert sorted(r.children or {}) == sorted(set(node["data"]) | set(sub))
+        for k, v in sub.items():
+            check(r.children[k], v)
+
+    @settings(max_examples=60, deadline=None)
+    @given(tree)
+    def run(node):
+        w = H5Writer()
+        put(w, None, node)
+        check(H5Reader(w.tobytes()).root, node)
+
+    run()
